@@ -1,0 +1,163 @@
+/* b200zk.h -- C ABI of libb200zk.so: B200 (sm_100a) Groth16 prover numerics.
+ *
+ * Drop-in boundary for the reference's (UrosTesic/zcash-gpu-thesis = librustzcash fork) prover hot path.
+ * The reference has no FFI for this path (its OpenCL experiments bypass the API); the boundary is the Rust
+ * signatures below, which a thin `-sys` crate binds to these entry points:
+ *
+ *   bellman/src/multiexp.rs:285-295   pub fn multiexp<Q,D,G,S>(pool, bases, density_map, exponents)
+ *   bellman/src/multiexp.rs:19-68     SourceBuilder / Source for (Arc<Vec<G>>, usize)
+ *   bellman/src/domain.rs:35-189      EvaluationDomain::{from_coeffs, fft, ifft, coset_fft, icoset_fft,
+ *                                     distribute_powers, z, divide_by_z_on_coset, mul_assign, sub_assign}
+ *   bellman/src/groth16/prover.rs:192-364  create_random_proof / create_proof (H-polynomial block :256-287)
+ *
+ * Conventions
+ *   - All integers are little-endian u64 limbs exactly as in Rust memory: FqRepr([u64;6]), FrRepr([u64;4]).
+ *     Field elements / point coordinates are in Montgomery form (what `Fq(FqRepr)` / `Fr(FrRepr)` hold);
+ *     MSM scalars are canonical `FrRepr` (what `into_repr()` returns, prover.rs:287).
+ *   - G1 affine = x||y (12 u64), G2 affine = x.c0||x.c1||y.c0||y.c1 (24 u64); the `infinity: bool` of
+ *     G1Affine/G2Affine (ec.rs:13-18) travels as a separate byte (or via a stride into the Rust struct).
+ *   - Projective results are Jacobian (X, Y, Z) Montgomery triples (18 / 36 u64) like `G1`/`G2` (ec.rs:20-24).
+ *     The representative is not unique; compare with the reference's PartialEq (ec.rs:45-85) or after
+ *     into_affine.  Field / affine / NTT outputs are canonical and bit-identical to the reference.
+ *   - No exceptions, no aborts: every call returns a status; b200zk_last_error() has the text.
+ *   - One context = one GPU + one CUDA stream.  Calls on one context are stream-ordered; use one context per
+ *     thread / in-flight future (the prover keeps 8 multiexps in flight, prover.rs:289-318).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry returns B200ZK_ERR_CUDA.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes; 1..3 map onto bellman's SynthesisError (bellman/src/lib.rs:171-188) */
+enum {
+    B200ZK_OK = 0,
+    B200ZK_ERR_UNEXPECTED_IDENTITY = 1, /* SynthesisError::UnexpectedIdentity   (multiexp.rs:48-50)  */
+    B200ZK_ERR_UNEXPECTED_EOF = 2,      /* SynthesisError::IoError(UnexpectedEof) (multiexp.rs:44-46) */
+    B200ZK_ERR_DEGREE_TOO_LARGE = 3,    /* SynthesisError::PolynomialDegreeTooLarge (domain.rs:59-61) */
+    B200ZK_ERR_BAD_ARG = 4,
+    B200ZK_ERR_CUDA = 5,
+    B200ZK_ERR_NCCL = 6
+};
+
+enum { B200ZK_G1 = 1, B200ZK_G2 = 2 };
+enum { B200ZK_FR = 0, B200ZK_FQ = 1 };
+/* EvaluationDomain transforms, domain.rs:83-132 */
+enum { B200ZK_FFT = 0, B200ZK_IFFT = 1, B200ZK_COSET_FFT = 2, B200ZK_ICOSET_FFT = 3 };
+/* element-wise field ops (fr.rs / fq.rs); used by the parity tests and by EvaluationDomain::{mul,sub}_assign */
+enum {
+    B200ZK_OP_ADD = 0, B200ZK_OP_SUB = 1, B200ZK_OP_MUL = 2, B200ZK_OP_SQUARE = 3, B200ZK_OP_DOUBLE = 4,
+    B200ZK_OP_NEGATE = 5, B200ZK_OP_INTO_REPR = 6, B200ZK_OP_FROM_REPR = 7, B200ZK_OP_INVERSE = 8
+};
+/* point ops (ec.rs:296-526) for the parity tests */
+enum { B200ZK_POINT_DOUBLE = 0, B200ZK_POINT_ADD = 1, B200ZK_POINT_ADD_MIXED = 2 };
+
+typedef struct b200zk_ctx b200zk_ctx;
+typedef struct b200zk_bases b200zk_bases;
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+/* Replaces Worker::new() (bellman/src/multicore.rs:24-31): a context owns one CUDA stream on `device`. */
+int b200zk_init(int device, b200zk_ctx **out);
+void b200zk_destroy(b200zk_ctx *ctx);
+const char *b200zk_last_error(b200zk_ctx *ctx);
+int b200zk_sync(b200zk_ctx *ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int b200zk_set_stream(b200zk_ctx *ctx, void *cuda_stream);
+int b200zk_device_count(void);
+int b200zk_sm_count(b200zk_ctx *ctx);
+const char *b200zk_version(void);
+
+/* device memory + timing helpers (so a host with no CUDA bindings can keep operands resident in HBM) */
+int b200zk_dev_alloc(b200zk_ctx *ctx, size_t bytes, void **dptr);
+int b200zk_dev_free(b200zk_ctx *ctx, void *dptr);
+int b200zk_h2d(b200zk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int b200zk_d2h(b200zk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int b200zk_host_alloc_pinned(size_t bytes, void **hptr);
+int b200zk_host_free_pinned(void *hptr);
+int b200zk_timer_start(b200zk_ctx *ctx);            /* cudaEventRecord on the context's stream */
+int b200zk_timer_stop(b200zk_ctx *ctx, float *ms);  /* record + synchronize + elapsed          */
+
+/* ---- bases (the SourceBuilder `(Arc<Vec<G>>, usize)`, multiexp.rs:34-68; ParameterSource, groth16/mod.rs:395-482) */
+/* Upload n affine bases once and keep them resident in HBM (the CRS is constant across proofs).
+ * `points` + i*stride -> x||y Montgomery limbs (96 B for G1, 192 B for G2); stride = 96/192 for packed arrays or
+ * sizeof(G1Affine)=104 / sizeof(G2Affine)=200 to read a Rust Vec<G1Affine> in place.
+ * `infinity` + i*inf_stride -> the `infinity: bool` byte, or NULL when no base is the identity. */
+int b200zk_bases_upload(b200zk_ctx *ctx, int group, const void *points, size_t n, size_t stride, const uint8_t *infinity,
+                        size_t inf_stride, b200zk_bases **out);
+/* Same from device memory (packed x||y, optional infinity bytes). The data is copied. */
+int b200zk_bases_from_device(b200zk_ctx *ctx, int group, const void *d_points, size_t n, const uint8_t *d_infinity, b200zk_bases **out);
+size_t b200zk_bases_len(const b200zk_bases *bases);
+void b200zk_bases_free(b200zk_bases *bases);
+
+/* ---- multiexp (bellman/src/multiexp.rs:285-335) ------------------------------------------------------------------ */
+/* result = sum over i with density[i] != 0 of scalars[i] * bases[base_offset + rank(i)], rank(i) = number of set
+ * density bytes before i (density == NULL is FullDensity: rank(i) = i).  Semantics of multiexp_inner
+ * (multiexp.rs:140-233): a zero scalar skips its base; a base at infinity that is *consumed* (non-zero scalar)
+ * -> UNEXPECTED_IDENTITY; running out of bases -> UNEXPECTED_EOF; the first offending exponent in iteration
+ * order decides which of the two is reported.  scalars: n_exp x 4 u64 canonical FrRepr.
+ * out_jacobian: 18 (G1) / 36 (G2) u64.  Synchronous: returns when the result is in `out_jacobian`. */
+int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                    const uint8_t *density, uint64_t *out_jacobian);
+/* Device-resident operands; result written to device memory, no host synchronisation (stream-ordered).
+ * The status word (0/1/2 as above) is written to d_status (4 bytes, device) and also folded into the next
+ * synchronous call's return value; pass NULL to ignore. */
+int b200zk_multiexp_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp,
+                        const uint8_t *d_density, void *d_out_jacobian, void *d_status);
+/* Pippenger window override for tuning (0 = automatic). */
+int b200zk_set_msm_window(b200zk_ctx *ctx, int window_bits);
+
+/* Sum of n Jacobian points (device, packed 144 / 288 B each) -> one Jacobian point (device). Used for the
+ * cross-GPU combine of per-shard partial sums and by tests (multiexp.rs:942-1200 reduction tests). */
+int b200zk_sum_points_dev(b200zk_ctx *ctx, int group, const void *d_points, size_t n, void *d_out);
+/* Jacobian -> affine on the device (ec.rs:586-619); out: x||y and one infinity byte per point. Host buffers. */
+int b200zk_into_affine(b200zk_ctx *ctx, int group, const uint64_t *jacobian, size_t n, uint64_t *out_xy, uint8_t *out_inf);
+
+/* Fixed-base batch multiplication out[i] = scalars[i] * base (ec.rs:87-99 semantics, windowed on the device).
+ * Generates CRS-like synthetic bases in HBM (generator.rs:266-288 uses wNAF tables for the same job).
+ * d_scalars: n x 4 u64 canonical, only the low `scalar_bits` bits are used; d_out_affine packed x||y. */
+int b200zk_fixed_base_mul_dev(b200zk_ctx *ctx, int group, const uint64_t *base_affine_host, const void *d_scalars, size_t n,
+                              uint32_t scalar_bits, void *d_out_affine, uint8_t *d_out_inf);
+
+/* ---- multi-GPU (one process per GPU; MSM sharded by base range, NCCL gather of the partial sums) ------------------- */
+/* Join an NCCL communicator. unique_id: 128 bytes from b200zk_nccl_unique_id() on rank 0, distributed by the launcher. */
+int b200zk_nccl_unique_id(uint8_t out_id[128]);
+int b200zk_comm_init(b200zk_ctx *ctx, const uint8_t unique_id[128], int rank, int world);
+/* Each rank passes the partial Jacobian sum of its shard (device); all ranks receive the total (device).
+ * ncclAllGather of 144/288 B per rank on the context's stream followed by a (world-1)-add kernel. */
+int b200zk_allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total);
+
+/* ---- EvaluationDomain (bellman/src/domain.rs) -------------------------------------------------------------------- */
+/* In-place transform of m = 2^log_m Montgomery Fr coefficients, natural order in and out (domain.rs:83-132).
+ * log_m >= 32 (= Fr::S) -> DEGREE_TOO_LARGE like from_coeffs (domain.rs:59-61). */
+int b200zk_ntt(b200zk_ctx *ctx, uint64_t *coeffs_host, uint32_t log_m, int kind);
+int b200zk_ntt_dev(b200zk_ctx *ctx, void *d_coeffs, uint32_t log_m, int kind);
+/* distribute_powers (domain.rs:105-118): coeffs[i] *= g^i, g given as 4 u64 Montgomery limbs (host). */
+int b200zk_distribute_powers_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_t g[4]);
+/* element-wise ops on device vectors of Fr/Fq elements: out[i] = op(a[i], b[i]) (b ignored for unary ops) */
+int b200zk_field_vec_dev(b200zk_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n);
+int b200zk_field_vec(b200zk_ctx *ctx, int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+/* coeffs[i] *= s (ifft's m^-1 scaling, divide_by_z_on_coset; domain.rs:88-103, 146-159) */
+int b200zk_fr_scale_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_t s[4]);
+/* point ops on host arrays (parity tests): a = Jacobian points; b = Jacobian (ADD) or affine x||y (ADD_MIXED) */
+int b200zk_point_op(b200zk_ctx *ctx, int group, int op, const uint64_t *a, const uint64_t *b, const uint8_t *b_inf, uint64_t *out, size_t n);
+
+/* The H-polynomial block of create_proof (prover.rs:256-287), fused on the device:
+ * a,b,c = evaluation vectors padded to m = 2^log_m (Montgomery); out = (m-1) x 4 u64 canonical coefficients
+ * (the `into_repr` exponents of the H multiexp).  a, b, c are clobbered in the _dev form. */
+int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_m, uint64_t *out);
+int b200zk_h_poly_dev(b200zk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_m, void *d_out);
+
+/* ---- calibration: integer-pipe roofline (SURVEY.md section 8d asks the build to measure it) -------------------------- */
+/* kind: 0 = IMAD (32-bit mad.lo), 1 = IMAD.WIDE (mad.wide.u32), 2 = IMAD.HI, 3 = IADD3 carry chain,
+ *       4 = Fq Montgomery multiply, 5 = Fr Montgomery multiply.  Returns operations per second over the whole GPU. */
+int b200zk_microbench(b200zk_ctx *ctx, int kind, int iters, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

@@ -1,0 +1,30 @@
+"""zcash-gpu-thesis_b200: B200-native (sm_100a CUDA) Groth16 prover numerics behind bellman's API.
+
+  csrc/         hand-written CUDA kernels + the C ABI (-> libb200zk.so, declared in include/b200zk.h)
+  bellman.py    host-side mirror of the reference interface (Worker, multiexp, EvaluationDomain, ...)
+
+The directory name has hyphens (it is the reference's name); import it as `zcash_gpu_thesis_b200`
+(the shim at the repo root) or through importlib.
+"""
+from . import _lib  # noqa: F401
+from .bellman import (  # noqa: F401
+    Bases,
+    CudaError,
+    DensityTracker,
+    DeviceBuffer,
+    EvaluationDomain,
+    FullDensity,
+    IoError,
+    PolynomialDegreeTooLarge,
+    SynthesisError,
+    UnexpectedIdentity,
+    Worker,
+    field_vec,
+    fixed_base_mul,
+    h_poly,
+    into_affine,
+    multiexp,
+    ntt_host,
+    point_op,
+)
+from ._lib import G1, G2, FR, FQ, FFT, IFFT, COSET_FFT, ICOSET_FFT  # noqa: F401

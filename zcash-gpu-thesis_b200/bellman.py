@@ -1,0 +1,463 @@
+"""Host-side mirror of the reference's operator interface for the prover hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference so the parity tests read like the
+reference's own tests:
+
+  bellman::multicore::Worker                      (bellman/src/multicore.rs:13-49)   -> Worker
+  bellman::multiexp::{multiexp, FullDensity,
+      DensityTracker, SourceBuilder}              (bellman/src/multiexp.rs:19-335)   -> multiexp, FullDensity, DensityTracker, Bases
+  bellman::domain::EvaluationDomain               (bellman/src/domain.rs:26-189)     -> EvaluationDomain
+  bellman::SynthesisError                         (bellman/src/lib.rs:171-188)       -> SynthesisError & subclasses
+
+All arrays are numpy uint64 in the reference's memory layout (little-endian limbs; Montgomery field elements,
+canonical FrRepr exponents).  All arithmetic happens on the GPU inside libb200zk.so; this file only moves
+buffers and maps status codes to exceptions.  It never imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+FR_MODULUS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+FR_S = 32  # fr.rs:47
+_FR_R = (1 << 256) % FR_MODULUS
+_FR_RINV = pow(_FR_R, -1, FR_MODULUS)
+
+
+class SynthesisError(Exception):
+    """bellman/src/lib.rs:171-188"""
+
+
+class UnexpectedIdentity(SynthesisError):
+    pass
+
+
+class IoError(SynthesisError):
+    """SynthesisError::IoError(UnexpectedEof): "expected more bases from source" (multiexp.rs:44-46)"""
+
+
+class PolynomialDegreeTooLarge(SynthesisError):
+    pass
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def _raise(worker, st):
+    msg = worker.last_error() if worker is not None else ""
+    if st == L.ERR_UNEXPECTED_IDENTITY:
+        raise UnexpectedIdentity(msg)
+    if st == L.ERR_UNEXPECTED_EOF:
+        raise IoError(msg or "expected more bases from source")
+    if st == L.ERR_DEGREE_TOO_LARGE:
+        raise PolynomialDegreeTooLarge(msg)
+    if st == L.ERR_BAD_ARG:
+        raise ValueError(msg)
+    raise CudaError(f"b200zk status {st}: {msg}")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if shape_last is not None:
+        a = a.reshape(-1, shape_last)
+    return a
+
+
+def fr_to_mont_limbs(x: int) -> np.ndarray:
+    m = (x * _FR_R) % FR_MODULUS
+    return np.array([(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+def fr_from_mont_limbs(l) -> int:
+    m = sum(int(v) << (64 * i) for i, v in enumerate(l))
+    return (m * _FR_RINV) % FR_MODULUS
+
+
+class DeviceBuffer:
+    """A cudaMalloc'd region owned by a Worker (operands stay resident in HBM between calls)."""
+
+    def __init__(self, worker, nbytes):
+        self.worker = worker
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        st = worker.lib.b200zk_dev_alloc(worker.ctx, self.nbytes, C.byref(p))
+        if st:
+            _raise(worker, st)
+        self.ptr = p.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        st = self.worker.lib.b200zk_h2d(self.worker.ctx, self.ptr, _ptr(arr), arr.nbytes)
+        if st:
+            _raise(self.worker, st)
+        self.worker.sync()  # the source array may be pageable / temporary
+        return self
+
+    def download(self, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        st = self.worker.lib.b200zk_d2h(self.worker.ctx, _ptr(out), self.ptr, out.nbytes)
+        if st:
+            _raise(self.worker, st)
+        return out
+
+    def free(self):
+        if self.ptr is not None and self.worker.ctx is not None:
+            self.worker.lib.b200zk_dev_free(self.worker.ctx, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Worker:
+    """bellman::multicore::Worker.  Here: one GPU + one CUDA stream (a b200zk context)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        ctx = C.c_void_p()
+        st = self.lib.b200zk_init(device, C.byref(ctx))
+        if st:
+            raise CudaError(f"b200zk_init(device={device}) failed with status {st}: no usable CUDA device (there is no CPU fallback)")
+        self.ctx = ctx
+        self.device = device
+
+    def last_error(self):
+        return (self.lib.b200zk_last_error(self.ctx) or b"").decode()
+
+    def sync(self):
+        st = self.lib.b200zk_sync(self.ctx)
+        if st:
+            _raise(self, st)
+
+    def sm_count(self):
+        return self.lib.b200zk_sm_count(self.ctx)
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, max(arr.nbytes, 1)).upload(arr)
+
+    def timer_start(self):
+        st = self.lib.b200zk_timer_start(self.ctx)
+        if st:
+            _raise(self, st)
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        st = self.lib.b200zk_timer_stop(self.ctx, C.byref(ms))
+        if st:
+            _raise(self, st)
+        return ms.value
+
+    def set_msm_window(self, c):
+        st = self.lib.b200zk_set_msm_window(self.ctx, c)
+        if st:
+            _raise(self, st)
+
+    def microbench(self, kind, iters=2000):
+        out = C.c_double()
+        st = self.lib.b200zk_microbench(self.ctx, kind, iters, C.byref(out))
+        if st:
+            _raise(self, st)
+        return out.value
+
+    def close(self):
+        if self.ctx is not None:
+            self.lib.b200zk_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------------ multiexp
+class FullDensity:
+    """multiexp.rs:78-97"""
+
+    def get_query_size(self):
+        return None
+
+
+class DensityTracker:
+    """multiexp.rs:99-138 (bit-vec storage expanded to one byte per exponent at the boundary)"""
+
+    def __init__(self, bits=None):
+        self.bv = [] if bits is None else [bool(b) for b in bits]
+        self.total_density = sum(self.bv)
+
+    def add_element(self):
+        self.bv.append(False)
+
+    def inc(self, idx):
+        if not self.bv[idx]:
+            self.bv[idx] = True
+            self.total_density += 1
+
+    def get_total_density(self):
+        return self.total_density
+
+    def get_query_size(self):
+        return len(self.bv)
+
+    def as_bytes(self):
+        return np.array(self.bv, dtype=np.uint8)
+
+
+class Bases:
+    """The base vector of a SourceBuilder `(Arc<Vec<G>>, usize)` kept resident in HBM (multiexp.rs:34-68)."""
+
+    def __init__(self, worker: Worker, group: int, xy, infinity=None, stride=None):
+        self.worker = worker
+        self.group = group
+        width = 12 if group == L.G1 else 24
+        xy = _u64(xy, width)
+        self.n = xy.shape[0]
+        inf = None if infinity is None else np.ascontiguousarray(infinity, dtype=np.uint8)
+        h = C.c_void_p()
+        st = worker.lib.b200zk_bases_upload(worker.ctx, group, _ptr(xy), self.n, width * 8, _ptr(inf), 1, C.byref(h))
+        if st:
+            _raise(worker, st)
+        self.handle = h
+
+    @classmethod
+    def from_device(cls, worker, group, dbuf, n, dinf=None):
+        self = cls.__new__(cls)
+        self.worker, self.group, self.n = worker, group, n
+        h = C.c_void_p()
+        st = worker.lib.b200zk_bases_from_device(worker.ctx, group, dbuf.ptr, n, None if dinf is None else dinf.ptr, C.byref(h))
+        if st:
+            _raise(worker, st)
+        self.handle = h
+        return self
+
+    def __len__(self):
+        return self.n
+
+    def free(self):
+        if getattr(self, "handle", None) is not None and self.worker.ctx is not None:
+            self.worker.lib.b200zk_bases_free(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def window_size_reference(n: int) -> int:
+    """The reference's window formula (multiexp.rs:296-300); used for the algorithmic-work accounting."""
+    return 3 if n < 32 else int(math.ceil(math.log(float(n))))
+
+
+def multiexp(pool: Worker, bases, density_map, exponents):
+    """bellman::multiexp::multiexp (multiexp.rs:285-335).
+
+    bases: a `Bases` or a `(Bases, offset)` SourceBuilder tuple; density_map: FullDensity or DensityTracker;
+    exponents: (n, 4) uint64 canonical FrRepr.  Returns the Jacobian result as 18 (G1) / 36 (G2) uint64.
+    Raises UnexpectedIdentity / IoError exactly where the reference's Source would (multiexp.rs:42-68).
+    """
+    if isinstance(bases, tuple):
+        bases, offset = bases
+    else:
+        offset = 0
+    exponents = _u64(exponents, 4)
+    n = exponents.shape[0]
+    density = None
+    if density_map is not None and density_map.get_query_size() is not None:
+        # multiexp.rs:302-307: the query size must match the number of exponents
+        assert density_map.get_query_size() == n
+        density = density_map.as_bytes()
+    out = np.zeros(18 if bases.group == L.G1 else 36, dtype=np.uint64)
+    st = pool.lib.b200zk_multiexp(pool.ctx, bases.handle, offset, _ptr(exponents), n, _ptr(density), _ptr(out))
+    if st:
+        _raise(pool, st)
+    return out
+
+
+def into_affine(pool: Worker, group: int, jacobian):
+    """CurveProjective::into_affine (ec.rs:586-619) on the device. Returns (xy array (n, 12|24), infinity flags)."""
+    w = 18 if group == L.G1 else 36
+    jac = _u64(jacobian, w)
+    n = jac.shape[0]
+    out = np.zeros((n, 12 if group == L.G1 else 24), dtype=np.uint64)
+    inf = np.zeros(n, dtype=np.uint8)
+    st = pool.lib.b200zk_into_affine(pool.ctx, group, _ptr(jac), n, _ptr(out), _ptr(inf))
+    if st:
+        _raise(pool, st)
+    return out, inf
+
+
+# ------------------------------------------------------------------------------------------------------ domain
+class EvaluationDomain:
+    """bellman::domain::EvaluationDomain<E, Scalar<E>> with the coefficients resident on the GPU."""
+
+    def __init__(self, worker, dbuf, m, exp):
+        self.worker, self.buf, self.m, self.exp = worker, dbuf, m, exp
+
+    @classmethod
+    def from_coeffs(cls, worker: Worker, coeffs):
+        """domain.rs:48-81: pad to m = 2^exp with zeros; PolynomialDegreeTooLarge when exp >= Fr::S."""
+        coeffs = _u64(coeffs, 4)
+        m, exp = 1, 0
+        while m < coeffs.shape[0]:
+            m *= 2
+            exp += 1
+            if exp >= FR_S:
+                raise PolynomialDegreeTooLarge()
+        padded = np.zeros((m, 4), dtype=np.uint64)
+        padded[: coeffs.shape[0]] = coeffs
+        return cls(worker, worker.to_device(padded), m, exp)
+
+    def __len__(self):
+        return self.m
+
+    def into_coeffs(self):
+        return self.buf.download(np.uint64, self.m * 4).reshape(self.m, 4)
+
+    def as_ref(self):
+        return self.into_coeffs()
+
+    def _ntt(self, kind):
+        st = self.worker.lib.b200zk_ntt_dev(self.worker.ctx, self.buf.ptr, self.exp, kind)
+        if st:
+            _raise(self.worker, st)
+
+    def fft(self, worker=None):
+        self._ntt(L.FFT)
+
+    def ifft(self, worker=None):
+        self._ntt(L.IFFT)
+
+    def coset_fft(self, worker=None):
+        self._ntt(L.COSET_FFT)
+
+    def icoset_fft(self, worker=None):
+        self._ntt(L.ICOSET_FFT)
+
+    def distribute_powers(self, worker, g: int):
+        gl = fr_to_mont_limbs(g % FR_MODULUS)
+        st = self.worker.lib.b200zk_distribute_powers_dev(self.worker.ctx, self.buf.ptr, self.m, _ptr(gl))
+        if st:
+            _raise(self.worker, st)
+
+    def z(self, tau: int) -> int:
+        """domain.rs:136-141: tau^m - 1"""
+        return (pow(tau, self.m, FR_MODULUS) - 1) % FR_MODULUS
+
+    def divide_by_z_on_coset(self, worker=None):
+        i = pow(self.z(7), -1, FR_MODULUS)  # multiplicative_generator() = 7 (fr.rs:38-44)
+        il = fr_to_mont_limbs(i)
+        st = self.worker.lib.b200zk_fr_scale_dev(self.worker.ctx, self.buf.ptr, self.m, _ptr(il))
+        if st:
+            _raise(self.worker, st)
+
+    def _vec(self, op, other):
+        assert self.m == other.m  # domain.rs:163, 179
+        st = self.worker.lib.b200zk_field_vec_dev(self.worker.ctx, L.FR, op, self.buf.ptr, other.buf.ptr, self.buf.ptr, self.m)
+        if st:
+            _raise(self.worker, st)
+
+    def mul_assign(self, worker, other):
+        self._vec(L.OP_MUL, other)
+
+    def sub_assign(self, worker, other):
+        self._vec(L.OP_SUB, other)
+
+
+def h_poly(worker: Worker, a, b, c):
+    """The H-polynomial block of create_proof (prover.rs:256-287), fused on the device.
+    a, b, c: evaluation vectors (n, 4) Montgomery; returns (m - 1, 4) canonical FrRepr limbs."""
+    a, b, c = _u64(a, 4), _u64(b, 4), _u64(c, 4)
+    n = max(a.shape[0], b.shape[0], c.shape[0])
+    m, exp = 1, 0
+    while m < n:
+        m *= 2
+        exp += 1
+        if exp >= FR_S:
+            raise PolynomialDegreeTooLarge()
+
+    def pad(v):
+        p = np.zeros((m, 4), dtype=np.uint64)
+        p[: v.shape[0]] = v
+        return p
+
+    out = np.zeros((max(m - 1, 0), 4), dtype=np.uint64)
+    st = worker.lib.b200zk_h_poly(worker.ctx, _ptr(pad(a)), _ptr(pad(b)), _ptr(pad(c)), exp, _ptr(out))
+    if st:
+        _raise(worker, st)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ test / bench helpers
+def field_vec(worker, field, op, a, b=None):
+    w = 4 if field == L.FR else 6
+    a = _u64(a, w)
+    b = None if b is None else _u64(b, w)
+    out = np.empty_like(a)
+    st = worker.lib.b200zk_field_vec(worker.ctx, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0])
+    if st:
+        _raise(worker, st)
+    return out
+
+
+def point_op(worker, group, op, a, b=None, b_inf=None):
+    w = 18 if group == L.G1 else 36
+    a = _u64(a, w)
+    n = a.shape[0]
+    if b is not None:
+        b = _u64(b, w if op == L.POINT_ADD else (12 if group == L.G1 else 24))
+    if b_inf is not None:
+        b_inf = np.ascontiguousarray(b_inf, dtype=np.uint8)
+    out = np.empty_like(a)
+    st = worker.lib.b200zk_point_op(worker.ctx, group, op, _ptr(a), _ptr(b), _ptr(b_inf), _ptr(out), n)
+    if st:
+        _raise(worker, st)
+    return out
+
+
+def ntt_host(worker, coeffs, kind):
+    """b200zk_ntt on a host array (copy in, transform, copy out)."""
+    a = _u64(coeffs, 4).copy()
+    m = a.shape[0]
+    exp = m.bit_length() - 1
+    assert 1 << exp == m
+    st = worker.lib.b200zk_ntt(worker.ctx, _ptr(a), exp, kind)
+    if st:
+        _raise(worker, st)
+    return a
+
+
+def fixed_base_mul(worker, group, base_xy, scalars, scalar_bits=255):
+    """out[i] = scalars[i] * base, computed and left on the device.  Returns (DeviceBuffer xy, DeviceBuffer inf, n)."""
+    scalars = _u64(scalars, 4)
+    n = scalars.shape[0]
+    base_xy = _u64(base_xy)
+    ds = worker.to_device(scalars)
+    pb = 96 if group == L.G1 else 192
+    dout = worker.alloc(max(n * pb, 1))
+    dinf = worker.alloc(max(n, 1))
+    st = worker.lib.b200zk_fixed_base_mul_dev(worker.ctx, group, _ptr(base_xy), ds.ptr, n, scalar_bits, dout.ptr, dinf.ptr)
+    if st:
+        _raise(worker, st)
+    worker.sync()
+    ds.free()
+    return dout, dinf, n

@@ -1,0 +1,510 @@
+// C ABI of libb200zk.so (include/b200zk.h): context / memory plumbing and the thin entry points that the
+// reference-side bindings call in place of bellman::multiexp::multiexp (multiexp.rs:285), the
+// EvaluationDomain methods (domain.rs:83-189) and the H block of create_proof (prover.rs:256-287).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+
+#include "internal.h"
+
+namespace b200zk {
+
+int set_error(Ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+int ensure_scratch(Ctx *ctx, void **buf, size_t *cur, size_t bytes) {
+    if (bytes <= *cur) return B200ZK_OK;
+    if (*buf) {
+        // earlier work on the stream may still use the old buffer
+        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        B200ZK_CUDA(ctx, cudaFree(*buf));
+        *buf = nullptr;
+        *cur = 0;
+    }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(buf, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        B200ZK_CUDA(ctx, cudaMalloc(buf, want));
+    }
+    *cur = want;
+    return B200ZK_OK;
+}
+
+// ---- NCCL through dlopen: the library has no link-time dependency on it; single-GPU users never load it
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, /* ncclUniqueId by value */ NcclId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static bool load_nccl(std::string &err) {
+    std::lock_guard<std::mutex> l(g_nccl_mu);
+    if (g_nccl.handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) { err = "NCCL symbols missing"; dlclose(h); return false; }
+    g_nccl.handle = h;
+    return true;
+}
+
+}  // namespace b200zk
+
+using namespace b200zk;
+
+struct b200zk_ctx : public Ctx {};
+struct b200zk_bases : public Bases {};
+
+#define CHECK_CTX(ctx) do { if (!(ctx)) return B200ZK_ERR_BAD_ARG; } while (0)
+#define USE_DEVICE(ctx) B200ZK_CUDA(ctx, cudaSetDevice((ctx)->device))
+
+extern "C" {
+
+const char *b200zk_version(void) { return "b200zk 0.1 (sm_100a)"; }
+
+int b200zk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b200zk_init(int device, b200zk_ctx **out) {
+    if (!out) return B200ZK_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return B200ZK_ERR_CUDA; }  // no CPU fallback
+    if (device < 0 || device >= n) return B200ZK_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return B200ZK_ERR_CUDA;
+    b200zk_ctx *ctx = new b200zk_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200ZK_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return B200ZK_OK;
+}
+
+void b200zk_destroy(b200zk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ntt_free_all_tables(ctx);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    cudaFree(ctx->gather_buf);
+    cudaFree(ctx->small_slot);
+    cudaFree(ctx->scratch);
+    cudaFree(ctx->scratch2);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *b200zk_last_error(b200zk_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int b200zk_sync(b200zk_ctx *ctx) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_set_stream(b200zk_ctx *ctx, void *cuda_stream) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return B200ZK_OK;
+}
+
+int b200zk_sm_count(b200zk_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int b200zk_dev_alloc(b200zk_ctx *ctx, size_t bytes, void **dptr) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+    return B200ZK_OK;
+}
+int b200zk_dev_free(b200zk_ctx *ctx, void *dptr) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200ZK_CUDA(ctx, cudaFree(dptr));
+    return B200ZK_OK;
+}
+int b200zk_h2d(b200zk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B200ZK_OK;
+}
+int b200zk_d2h(b200zk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+int b200zk_host_alloc_pinned(size_t bytes, void **hptr) { return cudaMallocHost(hptr, bytes ? bytes : 1) == cudaSuccess ? B200ZK_OK : B200ZK_ERR_CUDA; }
+int b200zk_host_free_pinned(void *hptr) { return cudaFreeHost(hptr) == cudaSuccess ? B200ZK_OK : B200ZK_ERR_CUDA; }
+
+int b200zk_timer_start(b200zk_ctx *ctx) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return B200ZK_OK;
+}
+int b200zk_timer_stop(b200zk_ctx *ctx, float *ms) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    B200ZK_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    B200ZK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return B200ZK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- bases
+static size_t point_bytes(int group) { return group == B200ZK_G1 ? 96 : 192; }
+
+int b200zk_bases_from_device(b200zk_ctx *ctx, int group, const void *d_points, size_t n, const uint8_t *d_infinity, b200zk_bases **out) {
+    CHECK_CTX(ctx);
+    if (!out || (group != B200ZK_G1 && group != B200ZK_G2)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group / out");
+    USE_DEVICE(ctx);
+    b200zk_bases *b = new b200zk_bases();
+    b->ctx = ctx; b->group = group; b->n = n; b->points = nullptr; b->infinity = nullptr;
+    size_t bytes = n * point_bytes(group);
+    if (cudaMalloc(&b->points, bytes ? bytes : 1) != cudaSuccess) { delete b; return set_error(ctx, B200ZK_ERR_CUDA, "cudaMalloc(bases) failed"); }
+    if (bytes) cudaMemcpyAsync(b->points, d_points, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (d_infinity && n) {
+        if (cudaMalloc((void **)&b->infinity, n) != cudaSuccess) { cudaFree(b->points); delete b; return set_error(ctx, B200ZK_ERR_CUDA, "cudaMalloc(inf) failed"); }
+        cudaMemcpyAsync(b->infinity, d_infinity, n, cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = b;
+    return B200ZK_OK;
+}
+
+int b200zk_bases_upload(b200zk_ctx *ctx, int group, const void *points, size_t n, size_t stride, const uint8_t *infinity, size_t inf_stride,
+                        b200zk_bases **out) {
+    CHECK_CTX(ctx);
+    if (!out || (group != B200ZK_G1 && group != B200ZK_G2)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group / out");
+    const size_t pb = point_bytes(group);
+    if (stride < pb) return set_error(ctx, B200ZK_ERR_BAD_ARG, "stride smaller than a point");
+    USE_DEVICE(ctx);
+    b200zk_bases *b = new b200zk_bases();
+    b->ctx = ctx; b->group = group; b->n = n; b->points = nullptr; b->infinity = nullptr;
+    if (cudaMalloc(&b->points, n ? n * pb : 1) != cudaSuccess) { delete b; return set_error(ctx, B200ZK_ERR_CUDA, "cudaMalloc(bases) failed"); }
+    if (n) {
+        // strided host layout (e.g. a Rust Vec<G1Affine>, 104 B records) -> packed device array
+        cudaError_t e = cudaMemcpy2DAsync(b->points, pb, points, stride, pb, n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(b->points); delete b; return set_error(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e)); }
+        bool any_inf = false;
+        if (infinity) {
+            if (inf_stride == 0) inf_stride = 1;
+            for (size_t i = 0; i < n && !any_inf; i++) any_inf = infinity[i * inf_stride] != 0;
+        }
+        if (any_inf) {
+            if (cudaMalloc((void **)&b->infinity, n) != cudaSuccess) { cudaFree(b->points); delete b; return set_error(ctx, B200ZK_ERR_CUDA, "cudaMalloc(inf) failed"); }
+            cudaMemcpy2DAsync(b->infinity, 1, infinity, inf_stride, 1, n, cudaMemcpyHostToDevice, ctx->stream);
+        }
+    }
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = b;
+    return B200ZK_OK;
+}
+
+size_t b200zk_bases_len(const b200zk_bases *bases) { return bases ? bases->n : 0; }
+
+void b200zk_bases_free(b200zk_bases *bases) {
+    if (!bases) return;
+    cudaSetDevice(bases->ctx->device);
+    cudaStreamSynchronize(bases->ctx->stream);
+    cudaFree(bases->points);
+    cudaFree(bases->infinity);
+    delete bases;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- multiexp
+static int g_window_override = 0;
+int b200zk_set_msm_window(b200zk_ctx *ctx, int window_bits) {
+    CHECK_CTX(ctx);
+    if (window_bits != 0 && (window_bits < 2 || window_bits > 24)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "window bits must be 0 or in [2, 24]");
+    g_window_override = window_bits;
+    return B200ZK_OK;
+}
+
+int b200zk_multiexp_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp,
+                        const uint8_t *d_density, void *d_out_jacobian, void *d_status) {
+    CHECK_CTX(ctx);
+    if (!bases || !d_out_jacobian || (n_exp && !d_scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    if (bases->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bases live on another device");
+    USE_DEVICE(ctx);
+    return msm_run(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jacobian, d_status, g_window_override);
+}
+
+int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                    const uint8_t *density, uint64_t *out_jacobian) {
+    CHECK_CTX(ctx);
+    if (!bases || !out_jacobian || (n_exp && !scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    USE_DEVICE(ctx);
+    const size_t jac_bytes = bases->group == B200ZK_G1 ? 144 : 288;
+    // staging: scalars | density | result | status
+    size_t sc_bytes = n_exp * 32, den_bytes = density ? n_exp : 0;
+    size_t o_den = (sc_bytes + 255) / 256 * 256, o_res = o_den + (den_bytes + 255) / 256 * 256, o_st = o_res + 512, total = o_st + 256;
+    int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, total);
+    if (rc) return rc;
+    char *s = (char *)ctx->scratch;
+    if (sc_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(s, scalars, sc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (den_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(s + o_den, density, den_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = msm_run(ctx, bases, base_offset, s, n_exp, density ? (const uint8_t *)(s + o_den) : nullptr, s + o_res, s + o_st, g_window_override);
+    if (rc) return rc;
+    uint32_t status = 0;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out_jacobian, s + o_res, jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(&status, s + o_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status, "UnexpectedIdentity: a base at infinity was consumed");
+    if (status == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status, "IoError(UnexpectedEof): expected more bases from source");
+    return B200ZK_OK;
+}
+
+int b200zk_sum_points_dev(b200zk_ctx *ctx, int group, const void *d_points, size_t n, void *d_out) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    return msm_sum_points(ctx, group, d_points, n, d_out);
+}
+
+int b200zk_into_affine(b200zk_ctx *ctx, int group, const uint64_t *jacobian, size_t n, uint64_t *out_xy, uint8_t *out_inf) {
+    CHECK_CTX(ctx);
+    if (group != B200ZK_G1 && group != B200ZK_G2) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
+    USE_DEVICE(ctx);
+    const size_t jb = group == B200ZK_G1 ? 144 : 288, ab = point_bytes(group);
+    size_t o_out = (n * jb + 255) / 256 * 256, o_inf = o_out + (n * ab + 255) / 256 * 256;
+    int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, o_inf + n + 256);
+    if (rc) return rc;
+    char *s = (char *)ctx->scratch;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s, jacobian, n * jb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = msm_into_affine(ctx, group, s, n, s + o_out, (uint8_t *)(s + o_inf));
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out_xy, s + o_out, n * ab, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_inf) B200ZK_CUDA(ctx, cudaMemcpyAsync(out_inf, s + o_inf, n, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_fixed_base_mul_dev(b200zk_ctx *ctx, int group, const uint64_t *base_affine_host, const void *d_scalars, size_t n, uint32_t scalar_bits,
+                              void *d_out_affine, uint8_t *d_out_inf) {
+    CHECK_CTX(ctx);
+    if (group != B200ZK_G1 && group != B200ZK_G2) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
+    USE_DEVICE(ctx);
+    int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, 256);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, base_affine_host, point_bytes(group), cudaMemcpyHostToDevice, ctx->stream));
+    return msm_fixed_base(ctx, group, ctx->scratch, d_scalars, n, scalar_bits, d_out_affine, d_out_inf);
+}
+
+// ---------------------------------------------------------------------------------------------------------------- multi-GPU
+int b200zk_nccl_unique_id(uint8_t out_id[128]) {
+    std::string err;
+    if (!load_nccl(err)) return B200ZK_ERR_NCCL;
+    NcclId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return B200ZK_ERR_NCCL;
+    memcpy(out_id, id.internal, 128);
+    return B200ZK_OK;
+}
+
+int b200zk_comm_init(b200zk_ctx *ctx, const uint8_t unique_id[128], int rank, int world) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    std::string err;
+    if (!load_nccl(err)) return set_error(ctx, B200ZK_ERR_NCCL, err);
+    if (world < 1 || rank < 0 || rank >= world) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad rank/world");
+    NcclId id;
+    memcpy(id.internal, unique_id, 128);
+    int r = g_nccl.CommInitRank(&ctx->nccl_comm, world, id, rank);
+    if (r != 0) return set_error(ctx, B200ZK_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    ctx->rank = rank;
+    ctx->world = world;
+    B200ZK_CUDA(ctx, cudaMalloc(&ctx->gather_buf, (size_t)world * 288));
+    return B200ZK_OK;
+}
+
+int b200zk_allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    const size_t jb = group == B200ZK_G1 ? 144 : 288;
+    if (ctx->world == 1 || !ctx->nccl_comm) {
+        if (ctx->world != 1) return set_error(ctx, B200ZK_ERR_NCCL, "communicator not initialised");
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(d_total, d_partial, jb, cudaMemcpyDeviceToDevice, ctx->stream));
+        return B200ZK_OK;
+    }
+    int r = g_nccl.AllGather(d_partial, ctx->gather_buf, jb, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream);
+    if (r != 0) return set_error(ctx, B200ZK_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    return msm_sum_points(ctx, group, ctx->gather_buf, (size_t)ctx->world, d_total);
+}
+
+// ---------------------------------------------------------------------------------------------------------------- domain
+int b200zk_ntt_dev(b200zk_ctx *ctx, void *d_coeffs, uint32_t log_m, int kind) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    return ntt_run(ctx, d_coeffs, log_m, kind);
+}
+
+int b200zk_ntt(b200zk_ctx *ctx, uint64_t *coeffs_host, uint32_t log_m, int kind) {
+    CHECK_CTX(ctx);
+    if (log_m >= 32) return set_error(ctx, B200ZK_ERR_DEGREE_TOO_LARGE, "log_m >= Fr::S (32)");
+    USE_DEVICE(ctx);
+    const size_t bytes = ((size_t)1 << log_m) * 32;
+    int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, bytes);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(ctx->scratch2, coeffs_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ntt_run(ctx, ctx->scratch2, log_m, kind);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(coeffs_host, ctx->scratch2, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+static int stage_small(b200zk_ctx *ctx, const uint64_t v[4], void **dptr) {
+    // a 32-byte constant staged at the end of the gather buffer area (own small allocation, stream ordered)
+    if (!ctx->small_slot) B200ZK_CUDA(ctx, cudaMalloc(&ctx->small_slot, 256));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(ctx->small_slot, v, 32, cudaMemcpyHostToDevice, ctx->stream));
+    *dptr = ctx->small_slot;
+    return B200ZK_OK;
+}
+
+int b200zk_distribute_powers_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_t g[4]) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    void *dg;
+    int rc = stage_small(ctx, g, &dg);
+    if (rc) return rc;
+    rc = ntt_distribute_powers(ctx, d_coeffs, n, dg);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `g` slot is reused by the next call
+    return B200ZK_OK;
+}
+
+int b200zk_fr_scale_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_t s[4]) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    void *ds;
+    int rc = stage_small(ctx, s, &ds);
+    if (rc) return rc;
+    rc = launch_fr_scale(ctx, d_coeffs, ds, n);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_field_vec_dev(b200zk_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    return launch_field_vec(ctx, field, op, d_a, d_b, d_out, n);
+}
+
+int b200zk_field_vec(b200zk_ctx *ctx, int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+    CHECK_CTX(ctx);
+    if (field != B200ZK_FR && field != B200ZK_FQ) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field");
+    USE_DEVICE(ctx);
+    const size_t eb = field == B200ZK_FR ? 32 : 48;
+    const size_t bytes = (n * eb + 255) / 256 * 256;
+    int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, 3 * bytes + 256);
+    if (rc) return rc;
+    char *s = (char *)ctx->scratch;
+    if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(s, a, n * eb, cudaMemcpyHostToDevice, ctx->stream));
+    if (n && b) B200ZK_CUDA(ctx, cudaMemcpyAsync(s + bytes, b, n * eb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_field_vec(ctx, field, op, s, b ? s + bytes : s, s + 2 * bytes, n);
+    if (rc) return rc;
+    if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(out, s + 2 * bytes, n * eb, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_point_op(b200zk_ctx *ctx, int group, int op, const uint64_t *a, const uint64_t *b, const uint8_t *b_inf, uint64_t *out, size_t n) {
+    CHECK_CTX(ctx);
+    if (group != B200ZK_G1 && group != B200ZK_G2) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
+    if (op < B200ZK_POINT_DOUBLE || op > B200ZK_POINT_ADD_MIXED) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad point op");
+    USE_DEVICE(ctx);
+    const size_t jb = group == B200ZK_G1 ? 144 : 288, ab = point_bytes(group);
+    const size_t bb = op == B200ZK_POINT_ADD ? jb : ab;
+    size_t o_b = (n * jb + 255) / 256 * 256, o_inf = o_b + (n * jb + 255) / 256 * 256, o_out = o_inf + (n + 255) / 256 * 256;
+    int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, o_out + n * jb + 256);
+    if (rc) return rc;
+    char *s = (char *)ctx->scratch;
+    if (n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s, a, n * jb, cudaMemcpyHostToDevice, ctx->stream));
+    if (op != B200ZK_POINT_DOUBLE) B200ZK_CUDA(ctx, cudaMemcpyAsync(s + o_b, b, n * bb, cudaMemcpyHostToDevice, ctx->stream));
+    if (op == B200ZK_POINT_ADD_MIXED && b_inf) B200ZK_CUDA(ctx, cudaMemcpyAsync(s + o_inf, b_inf, n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_point_op(ctx, group, op, s, s + o_b, (op == B200ZK_POINT_ADD_MIXED && b_inf) ? (const uint8_t *)(s + o_inf) : nullptr, s + o_out, n);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out, s + o_out, n * jb, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_h_poly_dev(b200zk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_m, void *d_out) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (log_m >= 32) return set_error(ctx, B200ZK_ERR_DEGREE_TOO_LARGE, "log_m >= Fr::S (32)");
+    return ntt_h_poly(ctx, d_a, d_b, d_c, log_m, d_out);
+}
+
+int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_m, uint64_t *out) {
+    CHECK_CTX(ctx);
+    if (log_m >= 32) return set_error(ctx, B200ZK_ERR_DEGREE_TOO_LARGE, "log_m >= Fr::S (32)");
+    USE_DEVICE(ctx);
+    const size_t bytes = ((size_t)1 << log_m) * 32;
+    int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, 4 * bytes);
+    if (rc) return rc;
+    char *s = (char *)ctx->scratch2;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s + bytes, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s + 2 * bytes, c, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ntt_h_poly(ctx, s, s + bytes, s + 2 * bytes, log_m, s + 3 * bytes);
+    if (rc) return rc;
+    if (bytes > 32) B200ZK_CUDA(ctx, cudaMemcpyAsync(out, s + 3 * bytes, bytes - 32, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- calibration
+int b200zk_microbench(b200zk_ctx *ctx, int kind, int iters, double *ops_per_s) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    if (iters < 1 || !ops_per_s) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad iters");
+    const int threads = 256, blocks = ctx->sm_count * 4;
+    int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, (size_t)threads * blocks * 4);
+    if (rc) return rc;
+    if ((rc = launch_microbench(ctx, kind, iters, blocks, threads, ctx->scratch))) return rc;  // warm-up
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if ((rc = launch_microbench(ctx, kind, iters, blocks, threads, ctx->scratch))) return rc;
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    B200ZK_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    B200ZK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    double per_thread = kind <= 3 ? 64.0 * iters : 2.0 * iters;
+    *ops_per_s = per_thread * threads * blocks / (ms * 1e-3);
+    return B200ZK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// Element-wise field / point kernels: the device twins of the reference's per-primitive OpenCL test kernels
+// (bellman/src/bls12-381.cl:799-887 test_fq_*, :1612-1700 test_fr_*, :1045-1170 test_projective_*), of
+// EvaluationDomain::{mul_assign, sub_assign} and the scaling loops (bellman/src/domain.rs:88-103, 146-189),
+// plus the integer-pipe calibration micro-benchmarks.
+#include "ec.cuh"
+#include "internal.h"
+
+namespace b200zk {
+
+template <class F>
+__global__ void k_field_vec(int op, const F *__restrict__ a, const F *__restrict__ b, F *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i];
+    F r;
+    switch (op) {
+    case B200ZK_OP_ADD: r = x + b[i]; break;
+    case B200ZK_OP_SUB: r = x - b[i]; break;
+    case B200ZK_OP_MUL: r = x * b[i]; break;
+    case B200ZK_OP_SQUARE: r = x.sqr(); break;
+    case B200ZK_OP_DOUBLE: r = x.dbl(); break;
+    case B200ZK_OP_NEGATE: r = x.neg(); break;
+    case B200ZK_OP_INTO_REPR: r = x.from_mont(); break;
+    case B200ZK_OP_FROM_REPR: r = x.to_mont(); break;
+    default: r = x.inverse(); break;
+    }
+    out[i] = r;
+}
+
+int launch_field_vec(Ctx *ctx, int field, int op, const void *a, const void *b, void *out, size_t n) {
+    if (n == 0) return B200ZK_OK;
+    if (op < 0 || op > B200ZK_OP_INVERSE) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field op");
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (field == B200ZK_FR)
+        k_field_vec<fr_t><<<blocks, 128, 0, ctx->stream>>>(op, (const fr_t *)a, (const fr_t *)b, (fr_t *)out, n);
+    else if (field == B200ZK_FQ)
+        k_field_vec<fq_t><<<blocks, 128, 0, ctx->stream>>>(op, (const fq_t *)a, (const fq_t *)b, (fq_t *)out, n);
+    else
+        return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field");
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+__global__ void k_fr_scale(fr_t *__restrict__ a, const fr_t *__restrict__ s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[i] = a[i] * s[0];
+}
+int launch_fr_scale(Ctx *ctx, void *a, const void *scalar_dev, size_t n) {
+    if (n == 0) return B200ZK_OK;
+    k_fr_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((fr_t *)a, (const fr_t *)scalar_dev, n);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// ---- point ops, one thread per element (ec.rs:296-526)
+template <class F>
+__global__ void k_point_op(int op, const Jacobian<F> *__restrict__ a, const void *__restrict__ b, const uint8_t *__restrict__ b_inf,
+                           Jacobian<F> *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jacobian<F> p = a[i];
+    if (op == B200ZK_POINT_DOUBLE) {
+        jacobian_double(p);
+    } else if (op == B200ZK_POINT_ADD) {
+        jacobian_add(p, ((const Jacobian<F> *)b)[i]);
+    } else {
+        jacobian_add_mixed(p, ((const Affine<F> *)b)[i], b_inf ? b_inf[i] != 0 : false);
+    }
+    out[i] = p;
+}
+int launch_point_op(Ctx *ctx, int group, int op, const void *a, const void *b, const uint8_t *b_inf, void *out, size_t n) {
+    if (n == 0) return B200ZK_OK;
+    unsigned blocks = (unsigned)((n + 63) / 64);
+    if (group == B200ZK_G1)
+        k_point_op<fq_t><<<blocks, 64, 0, ctx->stream>>>(op, (const g1_jac_t *)a, b, b_inf, (g1_jac_t *)out, n);
+    else if (group == B200ZK_G2)
+        k_point_op<fq2_t><<<blocks, 64, 0, ctx->stream>>>(op, (const g2_jac_t *)a, b, b_inf, (g2_jac_t *)out, n);
+    else
+        return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// ---- integer-pipe calibration -----------------------------------------------------------------------------------
+// Independent instruction streams (8 accumulators per thread) so the pipe, not latency, is measured.
+template <int KIND>
+__global__ void k_microbench(int iters, uint32_t seed, uint32_t *out) {
+    uint32_t x[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x[i] = seed + threadIdx.x * 8 + i; y[i] = seed * 3 + i; }
+    uint32_t m = seed | 1;
+    if (KIND == 0) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(m), "r"(y[i]));
+        }
+    } else if (KIND == 1) {
+        unsigned long long w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = x[i];
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(m), "r"(y[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32);
+    } else if (KIND == 2) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(m), "r"(y[i]));
+        }
+    } else if (KIND == 3) {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(x[0]) : "r"(y[0]));
+#pragma unroll
+                for (int i = 1; i < 7; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+                asm volatile("addc.u32 %0, %0, %1;" : "+r"(x[7]) : "r"(y[7]));
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= x[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <class F>
+__global__ void k_microbench_mul(int iters, uint32_t seed, uint32_t *out) {
+    F a = F::one(), b = F::r2();
+    a.v[0] ^= threadIdx.x;
+    b.v[1] ^= seed;
+    F c = a + b, d = a - b;
+    for (int it = 0; it < iters; it++) {  // two independent chains per thread
+        a = a * c;
+        b = b * d;
+    }
+    F r = a + b;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) acc ^= r.v[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// ops per launch are returned through *ops_per_launch so the caller can time with its own events
+int launch_microbench(Ctx *ctx, int kind, int iters, int blocks, int threads, void *out) {
+    uint32_t *o = (uint32_t *)out;
+    switch (kind) {
+    case 0: k_microbench<0><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, o); break;
+    case 1: k_microbench<1><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, o); break;
+    case 2: k_microbench<2><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, o); break;
+    case 3: k_microbench<3><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, o); break;
+    case 4: k_microbench_mul<fq_t><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, o); break;
+    case 5: k_microbench_mul<fr_t><<<blocks, threads, 0, ctx->stream>>>(iters, 12345u, o); break;
+    default: return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad microbench kind");
+    }
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk

@@ -1,0 +1,251 @@
+// Montgomery prime-field arithmetic for BLS12-381 Fr (8 x u32) and Fq (12 x u32) on sm_100a.
+//
+// Device counterpart of the reference's pairing::bls12_381::{fr,fq} (fr.rs:341-571, fq.rs:813-1123) and of
+// its limb primitives adc/sbb/mac_with_carry (pairing/src/lib.rs:645-679).  The reference works on 64-bit
+// limbs with u128 products; the B200 integer pipe is 32-bit (IMAD / IMAD.WIDE on the FMA pipe, IADD3 on
+// the ALU pipe), so elements are kept as N little-endian u32 limbs -- the *same bytes* as the reference's
+// [u64; N/2] -- and every operation returns the fully reduced canonical value in [0, p), exactly like the
+// reference (fq.rs:1023-1031 `reduce`), which is what makes results bit-identical.
+//
+// Multiplication is an operand-scanning Montgomery product with the partial products split into an
+// "even" and an "odd" accumulator so that each a_j*b_i (64-bit) lands on a 64-bit aligned pair and the
+// whole row is one mad.lo.cc/madc.hi.cc carry chain (ptxas fuses each pair into IMAD.WIDE.U32 + carry).
+// The per-row right shift by 32 bits is free: the accumulators swap roles every row.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200zk {
+
+// ------------------------------------------------------------------------------------------------ PTX carry helpers
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+// ------------------------------------------------------------------------------------------------ field parameters
+// Constants as in fr.rs:4-55 / fq.rs:5-42, split into u32 limbs.
+struct FrParams {
+    static constexpr int N = 8;
+    static constexpr uint32_t M0 = 0xffffffffu;  // -r^-1 mod 2^32 (low word of INV = 0xfffffffeffffffff)
+    __device__ __host__ static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return m[i];
+    }
+    __device__ __host__ static constexpr uint32_t one(int i) {  // R = 2^256 mod r
+        constexpr uint32_t m[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return m[i];
+    }
+    __device__ __host__ static constexpr uint32_t r2(int i) {  // R^2 mod r
+        constexpr uint32_t m[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return m[i];
+    }
+};
+struct FqParams {
+    static constexpr int N = 12;
+    static constexpr uint32_t M0 = 0xfffcfffdu;  // low word of INV = 0x89f3fffcfffcfffd
+    __device__ __host__ static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                    0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return m[i];
+    }
+    __device__ __host__ static constexpr uint32_t one(int i) {  // R = 2^384 mod q
+        constexpr uint32_t m[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                    0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return m[i];
+    }
+    __device__ __host__ static constexpr uint32_t r2(int i) {  // R^2 mod q
+        constexpr uint32_t m[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                    0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return m[i];
+    }
+};
+
+template <class P>
+struct __align__(16) Fp {
+    static constexpr int N = P::N;
+    uint32_t v[N];
+
+    __device__ __forceinline__ static Fp zero() { Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r; }
+    __device__ __forceinline__ static Fp one() { Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+        return r; }
+    __device__ __forceinline__ static Fp r2() { Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+        return r; }
+    __device__ __forceinline__ bool is_zero() const { uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= v[i];
+        return o == 0; }
+    __device__ __forceinline__ bool operator==(const Fp &b) const { uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i];
+        return o == 0; }
+    __device__ __forceinline__ bool operator!=(const Fp &b) const { return !(*this == b); }
+
+    // r = x - p if x >= p else x   (x < 2p)      -- fq.rs:1023-1031
+    __device__ __forceinline__ static void final_sub(uint32_t *x) {
+        uint32_t t[N];
+        t[0] = sub_cc(x[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(x[i], P::mod(i));
+        uint32_t borrow = subc(0, 0);  // 0xffffffff if x < p
+#pragma unroll
+        for (int i = 0; i < N; i++) x[i] = borrow ? x[i] : t[i];
+    }
+
+    // fq.rs:813-823
+    __device__ __forceinline__ friend Fp operator+(const Fp &a, const Fp &b) {
+        Fp r;
+        r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+        r.v[N - 1] = addc(a.v[N - 1], b.v[N - 1]);
+        final_sub(r.v);
+        return r;
+    }
+    // fq.rs:825-834
+    __device__ __forceinline__ friend Fp operator-(const Fp &a, const Fp &b) {
+        Fp r;
+        r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+        uint32_t borrow = subc(0, 0);
+        // add p back when the subtraction wrapped
+        r.v[0] = add_cc(r.v[0], P::mod(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(r.v[i], P::mod(i) & borrow);
+        r.v[N - 1] = addc(r.v[N - 1], P::mod(N - 1) & borrow);
+        return r;
+    }
+    __device__ __forceinline__ Fp dbl() const { return *this + *this; }  // fq.rs:836-842
+    __device__ __forceinline__ Fp neg() const {                          // fq.rs:1004-1010
+        Fp r;
+        r.v[0] = sub_cc(P::mod(0), v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = subc_cc(P::mod(i), v[i]);
+        r.v[N - 1] = subc(P::mod(N - 1), v[N - 1]);
+        uint32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) nz |= v[i];
+        uint32_t mask = nz ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] &= mask;
+        return r;
+    }
+
+    // ---- Montgomery product rows ---------------------------------------------------------------
+    // acc[j], acc[j+1] = lo/hi(a[j] * bi), j = 0, 2, ..  (a points at the even- or odd-indexed limbs)
+    __device__ __forceinline__ static void mul_n(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) { acc[j] = mul_lo(a[j], bi); acc[j + 1] = mul_hi(a[j], bi); }
+    }
+    // acc[j..j+1] += a[j] * bi, one carry chain; carry-out left in CC
+    __device__ __forceinline__ static void cmad_n(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+        acc[0] = mad_lo_cc(a[0], bi, acc[0]);
+        acc[1] = madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) { acc[j] = madc_lo_cc(a[j], bi, acc[j]); acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 1]); }
+    }
+    // same with the modulus (immediates); `odd` selects limbs 1,3,5.. of p
+    template <int ODD>
+    __device__ __forceinline__ static void cmad_mod(uint32_t *acc, uint32_t mi) {
+        acc[0] = mad_lo_cc(P::mod(ODD), mi, acc[0]);
+        acc[1] = madc_hi_cc(P::mod(ODD), mi, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) { acc[j] = madc_lo_cc(P::mod(j + ODD), mi, acc[j]); acc[j + 1] = madc_hi_cc(P::mod(j + ODD), mi, acc[j + 1]); }
+    }
+    // acc[j] = a[j]*bi + acc[j+2] (+ carry-in), i.e. accumulate while shifting acc down by two limbs (64 bits)
+    __device__ __forceinline__ static void madc_n_rshift(uint32_t *acc, const uint32_t *a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2) { acc[j] = madc_lo_cc(a[j], bi, acc[j + 2]); acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 3]); }
+        acc[N - 2] = madc_lo_cc(a[N - 2], bi, 0);
+        acc[N - 1] = madc_hi(a[N - 2], bi, 0);
+    }
+    // One row: T += a*bi; T += m*p; T >>= 32 (the shift is implicit: the caller swaps `even` and `odd`).
+    // Value represented: T = sum even[k] 2^(32k) + 2^32 * sum odd[k] 2^(32k).
+    __device__ __forceinline__ static void mad_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_t bi, bool first) {
+        if (first) {
+            mul_n(odd, a + 1, bi);
+            mul_n(even, a, bi);
+        } else {
+            even[0] = add_cc(even[0], odd[1]);   // stray limb of the previous row
+            madc_n_rshift(odd, a + 1, bi);       // absorbs that carry (odd[0] is one limb above even[0])
+            cmad_n(even, a, bi);
+            odd[N - 1] = addc(odd[N - 1], 0);
+        }
+        uint32_t mi = even[0] * P::M0;
+        cmad_mod<1>(odd, mi);
+        cmad_mod<0>(even, mi);
+        odd[N - 1] = addc(odd[N - 1], 0);
+    }
+
+    // fq.rs:910-963 mul_assign + fq.rs:1040-1123 mont_reduce  ->  a*b*R^-1 mod p, canonical
+    __device__ __forceinline__ friend Fp operator*(const Fp &a, const Fp &b) {
+        uint32_t even[N], odd[N];
+        // a's limbs interleave: even-indexed at a.v[0], a.v[2].. ; mul_n/cmad_n step by 2 from the pointer given
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            mad_n_redc(even, odd, a.v, b.v[i], i == 0);
+            mad_n_redc(odd, even, a.v, b.v[i + 1], false);
+        }
+        // merge: result = even + (odd >> 32) with odd[0] == 0 ... (here roles are back to the original names)
+        Fp r;
+        r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(even[i], odd[i + 1]);
+        r.v[N - 1] = addc(even[N - 1], 0);
+        final_sub(r.v);
+        return r;
+    }
+    __device__ __forceinline__ Fp sqr() const { return *this * *this; }  // fq.rs:965-1002
+
+    // Montgomery -> canonical (fr.rs:290-303 into_repr) and back (fr.rs:279-288 from_repr)
+    __device__ __forceinline__ Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
+    __device__ __forceinline__ Fp to_mont() const { return *this * r2(); }
+
+    // Field::pow (lib.rs:306-324) with a small exponent
+    __device__ Fp pow(uint64_t e) const {
+        Fp res = one();
+        bool found = false;
+        for (int i = 63; i >= 0; i--) {
+            bool bit = (e >> i) & 1;
+            if (found) res = res.sqr(); else found = bit;
+            if (bit) res = res * *this;
+        }
+        return res;
+    }
+    // inverse by Fermat (p-2).  Canonical, so it equals the reference's binary EEA (fq.rs:849-903).  0 -> 0.
+    __device__ Fp inverse() const {
+        uint32_t e[N];
+        e[0] = P::mod(0) - 2;  // p is odd and p mod 2^32 >= 2 for both fields
+#pragma unroll
+        for (int i = 1; i < N; i++) e[i] = P::mod(i);
+        Fp res = one();
+        bool found = false;
+        for (int i = 32 * N - 1; i >= 0; i--) {
+            bool bit = (e[i >> 5] >> (i & 31)) & 1;
+            if (found) res = res.sqr(); else found = bit;
+            if (bit) res = res * *this;
+        }
+        return res;
+    }
+};
+
+typedef Fp<FrParams> fr_t;
+typedef Fp<FqParams> fq_t;
+
+}  // namespace b200zk

@@ -1,0 +1,89 @@
+// Internal declarations shared by the .cu translation units of libb200zk.so (not part of the C ABI).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zk.h"
+
+namespace b200zk {
+
+struct Ctx;
+
+// ---- error plumbing: every C-ABI entry returns an int status and records a message in the ctx
+int set_error(Ctx *ctx, int code, const std::string &msg);
+#define B200ZK_CUDA(ctx, call)                                                                                  \
+    do {                                                                                                        \
+        cudaError_t e__ = (call);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return b200zk::set_error(ctx, B200ZK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- cached per-domain-size NTT tables (device memory, Montgomery form)
+struct NttTables {
+    uint32_t log_n = 0;
+    void *tw = nullptr;        // omega^k,      k < n/2
+    void *tw_inv = nullptr;    // omega^-k,     k < n/2
+    void *g_lo = nullptr;      // g^j,          j < 2^LO_BITS
+    void *g_hi = nullptr;      // g^(j << LO_BITS)
+    void *gi_lo = nullptr;     // g^-j
+    void *gi_hi = nullptr;     // g^-(j << LO_BITS) * n^-1
+    void *consts = nullptr;    // fr_t[8]: omega, omega_inv, n_inv, g, g_inv, z_inv (1/(g^n - 1)), ...
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    std::string last_error;
+    std::mutex mu;
+    std::map<uint32_t, NttTables> ntt_tables;
+    // reusable scratch (grown on demand, stream-ordered use only)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *scratch2 = nullptr;
+    size_t scratch2_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // NCCL (loaded lazily, only when a communicator is requested)
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    void *gather_buf = nullptr;  // world * 288 B
+    void *small_slot = nullptr;  // 256 B staging for scalar constants
+};
+
+int ensure_scratch(Ctx *ctx, void **buf, size_t *cur, size_t bytes);
+
+struct Bases {
+    Ctx *ctx;
+    int group;          // 1 = G1 (96 B/point), 2 = G2 (192 B/point)
+    size_t n;
+    void *points;       // device, x||y Montgomery
+    uint8_t *infinity;  // device, n bytes, or nullptr when no base is the identity
+};
+
+// ---- launchers implemented in the .cu files (all enqueue on ctx->stream, no implicit sync)
+// field_kernels.cu
+int launch_field_vec(Ctx *ctx, int field, int op, const void *a, const void *b, void *out, size_t n);
+int launch_fr_scale(Ctx *ctx, void *a, const void *scalar_dev, size_t n);
+int launch_point_op(Ctx *ctx, int group, int op, const void *a, const void *b, const uint8_t *b_inf, void *out, size_t n);
+int launch_microbench(Ctx *ctx, int kind, int iters, int blocks, int threads, void *out);
+// ntt.cu
+int ntt_get_tables(Ctx *ctx, uint32_t log_n, NttTables **out);
+int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind);
+int ntt_distribute_powers(Ctx *ctx, void *d_coeffs, size_t n, const void *d_g);
+void ntt_free_all_tables(Ctx *ctx);
+int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *d_out_repr);
+// msm.cu
+int msm_run(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density,
+            void *d_out_jac, void *d_status_out, int window_bits);
+int msm_fixed_base(Ctx *ctx, int group, const void *d_base_affine, const void *d_scalars, size_t n, uint32_t scalar_bits, void *d_out_affine,
+                   uint8_t *d_out_inf);
+int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf);
+int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out);
+
+}  // namespace b200zk
