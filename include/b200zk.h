@@ -152,6 +152,12 @@ int b200zk_point_op(b200zk_ctx *ctx, int group, int op, const uint64_t *a, const
 int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_m, uint64_t *out);
 int b200zk_h_poly_dev(b200zk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_m, void *d_out);
 
+/* Per-kernel timing for the roofline report: when enabled, b200zk_multiexp(_dev) brackets its dominant kernel
+ * (bucket accumulation) with CUDA events on the context's stream; read() synchronises and returns the summed
+ * milliseconds and the number of launches since the last read. */
+int b200zk_profile_enable(b200zk_ctx *ctx, int on);
+int b200zk_profile_read(b200zk_ctx *ctx, double *accumulate_ms, int *launches);
+
 /* ---- calibration: integer-pipe roofline (SURVEY.md section 8d asks the build to measure it) -------------------------- */
 /* kind: 0 = IMAD (32-bit mad.lo), 1 = IMAD.WIDE (mad.wide.u32), 2 = IMAD.HI, 3 = IADD3 carry chain,
  *       4 = Fq Montgomery multiply, 5 = Fr Montgomery multiply.  Returns operations per second over the whole GPU. */

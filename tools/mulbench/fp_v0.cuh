@@ -11,11 +11,11 @@
 // "even" and an "odd" accumulator so that each a_j*b_i (64-bit) lands on a 64-bit aligned pair and the
 // whole row is one mad.lo.cc/madc.hi.cc carry chain (ptxas fuses each pair into IMAD.WIDE.U32 + carry).
 // The per-row right shift by 32 bits is free: the accumulators swap roles every row.
-#pragma once
+
 #include <cstdint>
 #include <cuda_runtime.h>
 
-namespace b200zk {
+namespace v0 {
 
 // ------------------------------------------------------------------------------------------------ PTX carry helpers
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -177,30 +177,14 @@ struct __align__(16) Fp {
     }
     // One row: T += a*bi; T += m*p; T >>= 32 (the shift is implicit: the caller swaps `even` and `odd`).
     // Value represented: T = sum even[k] 2^(32k) + 2^32 * sum odd[k] 2^(32k).
-    // The a*bi products are formed with mul.wide.u32 (IMAD.WIDE, full rate on sm_100a -- measured 18.3 T/s,
-    // same as 32-bit IMAD, while IMAD.HI runs at 0.41x) and added with IADD3.X chains on the ALU pipe; the
-    // m*p products ride mad.lo.cc/madc.hi.cc pairs that ptxas fuses into IMAD.WIDE.U32.X.  Both pipes end up
-    // with ~300 instructions per Fq product (the all-mad.cc form made ptxas emit IMAD + IMAD.HI pairs).
-    __device__ __forceinline__ static void mulwide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
-        unsigned long long t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
-        lo = (uint32_t)t; hi = (uint32_t)(t >> 32);
-    }
     __device__ __forceinline__ static void mad_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_t bi, bool first) {
-        uint32_t pe[N], po[N];
-#pragma unroll
-        for (int j = 0; j < N; j += 2) { mulwide(pe[j], pe[j + 1], a[j], bi); mulwide(po[j], po[j + 1], a[j + 1], bi); }
         if (first) {
-#pragma unroll
-            for (int j = 0; j < N; j++) { even[j] = pe[j]; odd[j] = po[j]; }
+            mul_n(odd, a + 1, bi);
+            mul_n(even, a, bi);
         } else {
-            even[0] = add_cc(even[0], odd[1]);
-#pragma unroll
-            for (int j = 0; j < N - 2; j++) odd[j] = addc_cc(odd[j + 2], po[j]);
-            odd[N - 2] = addc_cc(po[N - 2], 0);
-            odd[N - 1] = addc(po[N - 1], 0);
-            even[0] = add_cc(even[0], pe[0]);
-#pragma unroll
-            for (int j = 1; j < N; j++) even[j] = addc_cc(even[j], pe[j]);
+            even[0] = add_cc(even[0], odd[1]);   // stray limb of the previous row
+            madc_n_rshift(odd, a + 1, bi);       // absorbs that carry (odd[0] is one limb above even[0])
+            cmad_n(even, a, bi);
             odd[N - 1] = addc(odd[N - 1], 0);
         }
         uint32_t mi = even[0] * P::M0;
@@ -208,6 +192,7 @@ struct __align__(16) Fp {
         cmad_mod<0>(even, mi);
         odd[N - 1] = addc(odd[N - 1], 0);
     }
+
     // fq.rs:910-963 mul_assign + fq.rs:1040-1123 mont_reduce  ->  a*b*R^-1 mod p, canonical
     __device__ __forceinline__ friend Fp operator*(const Fp &a, const Fp &b) {
         uint32_t even[N], odd[N];
@@ -246,10 +231,9 @@ struct __align__(16) Fp {
     // inverse by Fermat (p-2).  Canonical, so it equals the reference's binary EEA (fq.rs:849-903).  0 -> 0.
     __device__ Fp inverse() const {
         uint32_t e[N];
-        e[0] = sub_cc(P::mod(0), 2);  // p - 2 (Fr's low word is 1: the borrow must ripple)
+        e[0] = P::mod(0) - 2;  // p is odd and p mod 2^32 >= 2 for both fields
 #pragma unroll
-        for (int i = 1; i < N - 1; i++) e[i] = subc_cc(P::mod(i), 0);
-        e[N - 1] = subc(P::mod(N - 1), 0);
+        for (int i = 1; i < N; i++) e[i] = P::mod(i);
         Fp res = one();
         bool found = false;
         for (int i = 32 * N - 1; i >= 0; i--) {
@@ -264,4 +248,4 @@ struct __align__(16) Fp {
 typedef Fp<FrParams> fr_t;
 typedef Fp<FqParams> fq_t;
 
-}  // namespace b200zk
+}  // namespace v0

@@ -11,11 +11,11 @@
 // "even" and an "odd" accumulator so that each a_j*b_i (64-bit) lands on a 64-bit aligned pair and the
 // whole row is one mad.lo.cc/madc.hi.cc carry chain (ptxas fuses each pair into IMAD.WIDE.U32 + carry).
 // The per-row right shift by 32 bits is free: the accumulators swap roles every row.
-#pragma once
+
 #include <cstdint>
 #include <cuda_runtime.h>
 
-namespace b200zk {
+namespace v1 {
 
 // ------------------------------------------------------------------------------------------------ PTX carry helpers
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -264,4 +264,4 @@ struct __align__(16) Fp {
 typedef Fp<FrParams> fr_t;
 typedef Fp<FqParams> fq_t;
 
-}  // namespace b200zk
+}  // namespace v1

@@ -487,6 +487,29 @@ int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const u
     return B200ZK_OK;
 }
 
+int b200zk_profile_enable(b200zk_ctx *ctx, int on) {
+    CHECK_CTX(ctx);
+    ctx->prof_on = on != 0;
+    return B200ZK_OK;
+}
+int b200zk_profile_read(b200zk_ctx *ctx, double *accumulate_ms, int *launches) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double total = 0;
+    int n = 0;
+    for (auto &pr : ctx->prof_events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { total += ms; n++; }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->prof_events.clear();
+    if (accumulate_ms) *accumulate_ms = total;
+    if (launches) *launches = n;
+    return B200ZK_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- calibration
 int b200zk_microbench(b200zk_ctx *ctx, int kind, int iters, double *ops_per_s) {
     CHECK_CTX(ctx);

@@ -6,6 +6,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200zk.h"
@@ -54,6 +55,8 @@ struct Ctx {
     int rank = 0, world = 1;
     void *gather_buf = nullptr;  // world * 288 B
     void *small_slot = nullptr;  // 256 B staging for scalar constants
+    bool prof_on = false;        // bracket the dominant MSM kernel with events
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
 int ensure_scratch(Ctx *ctx, void **buf, size_t *cur, size_t bytes);

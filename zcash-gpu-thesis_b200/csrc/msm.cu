@@ -1,423 +1,36 @@
-// Pippenger multi-scalar multiplication over BLS12-381 G1 / G2 on sm_100a: the device implementation of
-// bellman::multiexp (bellman/src/multiexp.rs:140-335).
-//
-// The reference runs one CPU task per c-bit window; each task walks all (exponent, density) pairs, adds the
-// consumed base into bucket[digit-1] with a mixed Jacobian add (multiexp.rs:174-196), folds the buckets with
-// a running sum (multiexp.rs:202-206) and the windows are joined by c doublings each (multiexp.rs:223-229).
-// The B200 pipeline keeps the same decomposition (windows x buckets) but turns the scalar loop inside out:
-//
-//   1. k_msm_digits<COUNT>   per exponent: density rank -> base index, error detection (EOF / identity, the
-//                            Source semantics of multiexp.rs:42-68), signed c-bit digits; histogram per
-//                            (window, bucket) with global reductions
-//   2. scan                  exclusive prefix sum of the histogram = bucket offsets
-//   3. k_msm_digits<SCATTER> counting-sort of (base index, sign) by bucket
-//   4. k_msm_accumulate      one thread per bucket, XYZZ accumulator in registers, mixed adds (the hot loop)
-//   5. k_msm_reduce_level    bucket reduction sum (i+1)*S_i as a 32-ary tree of (R, A) pairs
-//   6. k_msm_window_combine  Horner over the windows (c doublings each), Jacobian result + status word
-//
-// Signed digits halve the bucket count (bucket ids 1..2^(c-1), negative digits add -P).  exp == 0 is skipped
-// and exp == 1 needs no special case: it is digit 1 of window 0.  The group result equals the reference's;
-// the Jacobian representative differs (see ec.cuh), parity is checked after into_affine.
-#include <algorithm>
-
-#include "ec.cuh"
+// Group dispatch for the MSM pipeline (the kernels live in msm_impl.cuh, instantiated by msm_g1.cu / msm_g2.cu).
 #include "internal.h"
 
 namespace b200zk {
 
-static constexpr uint32_t NO_POS = 0xffffffffu;
-
-// ------------------------------------------------------------------------------------------------ u32 exclusive scan
-// 3-kernel scan (block sums, scan of block sums, block scan + offset); input is u32 counts or u8 density flags.
-static constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
-
-template <class T>
-__device__ __forceinline__ uint32_t scan_val(const T *in, size_t i, size_t n) {
-    if (i >= n) return 0;
-    if (sizeof(T) == 1) return in[i] != 0 ? 1u : 0u;
-    return (uint32_t)in[i];
-}
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total) {
-    __shared__ uint32_t warp_sums[32];
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t x = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += y; }
-        warp_sums[lane] = s;
-    }
-    __syncthreads();
-    uint32_t base = wid ? warp_sums[wid - 1] : 0;
-    if (total) *total = warp_sums[(blockDim.x >> 5) - 1];
-    return base + x - v;
-}
-template <class T>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(const T *__restrict__ in, size_t n, uint32_t *__restrict__ sums) {
-    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) s += scan_val(in, base + i, n);
-    uint32_t total;
-    block_excl_scan(s, &total);
-    if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t *sums, size_t nblocks, uint32_t *total_out) {
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (size_t b0 = 0; b0 < nblocks; b0 += 1024) {
-        size_t i = b0 + threadIdx.x;
-        uint32_t v = i < nblocks ? sums[i] : 0;
-        uint32_t total;
-        uint32_t ex = block_excl_scan(v, &total);
-        uint32_t c = carry;
-        if (i < nblocks) sums[i] = c + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry = c + total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
-template <class T>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const T *__restrict__ in, size_t n, const uint32_t *__restrict__ sums,
-                                                            uint32_t *__restrict__ out, uint32_t *__restrict__ out2) {
-    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS], s = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { v[i] = scan_val(in, base + i, n); s += v[i]; }
-    uint32_t ex = block_excl_scan(s, nullptr) + sums[blockIdx.x];
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (base + i < n) { out[base + i] = ex; if (out2) out2[base + i] = ex; }
-        ex += v[i];
-    }
-}
-// out[i] = exclusive prefix of in; out[n] (and *total) = sum.  `sums` needs ceil(n / SCAN_BLOCK) + 1 words.
-template <class T>
-static void scan_u32(cudaStream_t st, const T *in, size_t n, uint32_t *out, uint32_t *out2, uint32_t *sums) {
-    if (n == 0) { cudaMemsetAsync(out, 0, sizeof(uint32_t), st); if (out2) cudaMemsetAsync(out2, 0, sizeof(uint32_t), st); return; }
-    size_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    k_scan_block_sums<T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums);
-    k_scan_sums<<<1, 1024, 0, st>>>(sums, nb, out + n);
-    k_scan_apply<T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums, out, out2);
-    if (out2) cudaMemcpyAsync(out2 + n, out + n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
-}
-
-// ------------------------------------------------------------------------------------------------ digits / sort
-struct MsmShape {
-    uint32_t c, W, B;  // window bits, windows (c*W >= 256), buckets per window = 2^(c-1)
-};
-
-__device__ __forceinline__ uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
-    uint32_t limb = pos >> 5, sh = pos & 31;
-    if (limb >= 8) return 0;
-    uint64_t v = s[limb];
-    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
-    return (uint32_t)(v >> sh) & ((1u << c) - 1);
-}
-
-// MODE 0: histogram, 1: scatter.  One thread per exponent (multiexp.rs:174-196 turned inside out).
-template <int MODE>
-__global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__ scalars, size_t n_exp, const uint8_t *__restrict__ density,
-                                                   const uint32_t *__restrict__ rank, size_t base_offset, size_t n_bases,
-                                                   const uint8_t *__restrict__ base_inf, MsmShape sh, uint32_t *__restrict__ counts_or_cursor,
-                                                   uint32_t *__restrict__ sorted, uint32_t *__restrict__ status) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_exp) return;
-    if (density && !density[i]) return;  // no base consumed (multiexp.rs:175)
-    size_t idx = base_offset + (rank ? rank[i] : i);
-    if (idx >= n_bases) {  // Source::{skip, add_assign_mixed} both fail first on an exhausted source (multiexp.rs:44, 60)
-        if (MODE == 0) atomicMin(&status[0], (uint32_t)i);
-        return;
-    }
-    uint32_t s[8];
-    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + 8 * i);
-    uint4 lo = sp[0], hi = sp[1];
-    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;  // exp == zero: skip(1)
-    if (base_inf && base_inf[idx]) {  // consumed identity base (multiexp.rs:48-50)
-        if (MODE == 0) atomicMin(&status[1], (uint32_t)i);
-        return;
-    }
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < sh.W; w++) {
-        uint32_t raw = extract_bits(s, w * sh.c, sh.c) + carry;
-        uint32_t neg = raw > sh.B;
-        uint32_t d = neg ? (1u << sh.c) - raw : raw;
-        carry = neg;
-        if (d == 0) continue;
-        uint32_t slot = w * sh.B + d - 1;
-        if (MODE == 0) {
-            atomicAdd(&counts_or_cursor[slot], 1u);
-        } else {
-            uint32_t pos = atomicAdd(&counts_or_cursor[slot], 1u);
-            sorted[pos] = (uint32_t)idx | (neg << 31);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ bucket accumulation
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                                                       const uint32_t *__restrict__ offsets, uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_buckets) return;
-    uint32_t beg = offsets[t], end = offsets[t + 1];
-    XYZZ<F> acc = XYZZ<F>::zero();
-    for (uint32_t k = beg; k < end; k++) {
-        uint32_t e = sorted[k];
-        Affine<F> p = bases[e & 0x7fffffffu];
-        acc.add_mixed(p, (e >> 31) != 0);
-    }
-    buckets[t] = acc;
-}
-
-// ------------------------------------------------------------------------------------------------ bucket reduction
-// For a range [lo, hi) of buckets: R = sum S_i, A = sum (i - lo) S_i.  A parent over K children of length `len`:
-// R = sum R_j, A = sum A_j + len * sum j R_j (running sum, then log2(len) doublings).  Window sum = A + R.
-static constexpr uint32_t RED_K = 32;
-template <class F>
-__global__ void __launch_bounds__(64) k_msm_reduce_level(const XYZZ<F> *__restrict__ inR, const XYZZ<F> *__restrict__ inA, uint32_t n_in,
-                                                        XYZZ<F> *__restrict__ outR, XYZZ<F> *__restrict__ outA, uint32_t n_out, uint32_t W,
-                                                        uint32_t log_len) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_out * W) return;
-    uint32_t w = t / n_out, p = t % n_out;
-    uint32_t first = p * RED_K, last = first + RED_K < n_in ? first + RED_K : n_in;
-    const XYZZ<F> *R = inR + (size_t)w * n_in;
-    XYZZ<F> run = XYZZ<F>::zero(), accw = XYZZ<F>::zero();
-    for (uint32_t j = last; j-- > first + 1;) {
-        run.add(R[j]);
-        accw.add(run);
-    }
-    run.add(R[first]);
-    for (uint32_t d = 0; d < log_len; d++) accw.dbl();
-    if (inA) {
-        const XYZZ<F> *A = inA + (size_t)w * n_in;
-        for (uint32_t j = first; j < last; j++) accw.add(A[j]);
-    }
-    outR[t] = run;
-    outA[t] = accw;
-}
-
-// multiexp.rs:223-229: higher = 2^c * higher + this, from the top window down; then the status word.
-template <class F>
-__global__ void k_msm_window_combine(const XYZZ<F> *__restrict__ R, const XYZZ<F> *__restrict__ A, MsmShape sh, Jacobian<F> *__restrict__ out,
-                                     uint32_t *__restrict__ status, uint32_t *__restrict__ status_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    XYZZ<F> acc = XYZZ<F>::zero();
-    for (uint32_t w = sh.W; w-- > 0;) {
-        for (uint32_t d = 0; d < sh.c; d++) acc.dbl();
-        XYZZ<F> t = A[w];
-        t.add(R[w]);
-        acc.add(t);
-    }
-    *out = acc.to_jacobian();
-    uint32_t eof = status[0], ident = status[1];
-    uint32_t st = B200ZK_OK;
-    if (eof != NO_POS || ident != NO_POS) st = eof < ident ? B200ZK_ERR_UNEXPECTED_EOF : B200ZK_ERR_UNEXPECTED_IDENTITY;
-    status[2] = st;
-    if (status_out) *status_out = st;
-}
-
-template <class F>
-__global__ void k_write_zero_point(Jacobian<F> *out, uint32_t *status, uint32_t *status_out) {
-    *out = Jacobian<F>::zero();
-    status[2] = 0;
-    if (status_out) *status_out = 0;
-}
-
-uint32_t msm_default_window(size_t n) {
-    if (n < (1u << 7)) return 4;
-    if (n < (1u << 10)) return 7;
-    if (n < (1u << 12)) return 8;
-    if (n < (1u << 14)) return 10;
-    if (n < (1u << 16)) return 11;
-    if (n < (1u << 18)) return 12;
-    if (n < (1u << 20)) return 13;
-    if (n < (1u << 22)) return 14;
-    if (n < (1u << 23)) return 15;
-    return 16;
-}
-
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-template <class F>
-static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density,
-                     void *d_out_jac, void *d_status_out, int window_bits) {
-    cudaStream_t st = ctx->stream;
-    if (n_exp >= (1ull << 31) || bases->n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "n >= 2^31 not supported");
-    MsmShape sh;
-    sh.c = window_bits > 0 ? (uint32_t)window_bits : msm_default_window(n_exp);
-    if (sh.c < 2 || sh.c > 24) return set_error(ctx, B200ZK_ERR_BAD_ARG, "window bits must be in [2, 24]");
-    sh.W = (256 + sh.c - 1) / sh.c;
-    sh.B = 1u << (sh.c - 1);
-    const size_t nbk = (size_t)sh.W * sh.B;
-    if (nbk + n_exp * sh.W >= (1ull << 32)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "n * windows >= 2^32 not supported");
-
-    // workspace carve-up
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_status = take(4 * sizeof(uint32_t));
-    size_t o_counts = take((nbk + 1) * sizeof(uint32_t));
-    size_t o_offsets = take((nbk + 1) * sizeof(uint32_t));
-    size_t o_cursor = take((nbk + 1) * sizeof(uint32_t));
-    size_t o_sums = take((std::max(nbk, n_exp) / SCAN_BLOCK + 2) * sizeof(uint32_t));
-    size_t o_rank = take(d_density ? (n_exp + 1) * sizeof(uint32_t) : 0);
-    size_t o_sorted = take(n_exp * sh.W * sizeof(uint32_t));
-    size_t o_buckets = take(nbk * sizeof(XYZZ<F>));
-    size_t lvl_entries = (size_t)sh.W * ((sh.B + RED_K - 1) / RED_K);
-    size_t o_r0 = take(lvl_entries * sizeof(XYZZ<F>)), o_a0 = take(lvl_entries * sizeof(XYZZ<F>));
-    size_t o_r1 = take(lvl_entries * sizeof(XYZZ<F>)), o_a1 = take(lvl_entries * sizeof(XYZZ<F>));
-    int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, off);
-    if (rc) return rc;
-    char *ws = (char *)ctx->scratch2;
-    uint32_t *status = (uint32_t *)(ws + o_status), *counts = (uint32_t *)(ws + o_counts), *offsets = (uint32_t *)(ws + o_offsets);
-    uint32_t *cursor = (uint32_t *)(ws + o_cursor), *sums = (uint32_t *)(ws + o_sums), *rank = d_density ? (uint32_t *)(ws + o_rank) : nullptr;
-    uint32_t *sorted = (uint32_t *)(ws + o_sorted);
-    XYZZ<F> *buckets = (XYZZ<F> *)(ws + o_buckets);
-    XYZZ<F> *lr[2] = {(XYZZ<F> *)(ws + o_r0), (XYZZ<F> *)(ws + o_r1)}, *la[2] = {(XYZZ<F> *)(ws + o_a0), (XYZZ<F> *)(ws + o_a1)};
-
-    B200ZK_CUDA(ctx, cudaMemsetAsync(status, 0xff, 2 * sizeof(uint32_t), st));
-    if (n_exp == 0) {
-        k_write_zero_point<F><<<1, 1, 0, st>>>((Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
-        B200ZK_CUDA(ctx, cudaGetLastError());
-        return B200ZK_OK;
-    }
-    B200ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (nbk + 1) * sizeof(uint32_t), st));
-    if (d_density) scan_u32<uint8_t>(st, d_density, n_exp, rank, nullptr, sums);
-    const unsigned eb = (unsigned)((n_exp + 255) / 256);
-    k_msm_digits<0><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, counts,
-                                        nullptr, status);
-    scan_u32<uint32_t>(st, counts, nbk, offsets, cursor, sums);
-    k_msm_digits<1><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, cursor,
-                                        sorted, status);
-    k_msm_accumulate<F><<<(unsigned)((nbk + 127) / 128), 128, 0, st>>>((const Affine<F> *)bases->points, sorted, offsets, (uint32_t)nbk, buckets);
-    // reduction tree
-    const XYZZ<F> *inR = buckets, *inA = nullptr;
-    uint32_t n_in = sh.B, log_len = 0;
-    int pp = 0;
-    do {
-        uint32_t n_out = (n_in + RED_K - 1) / RED_K;
-        uint32_t threads = n_out * sh.W;
-        k_msm_reduce_level<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, n_in, lr[pp], la[pp], n_out, sh.W, log_len);
-        inR = lr[pp]; inA = la[pp];
-        pp ^= 1;
-        n_in = n_out;
-        log_len += 5;
-    } while (n_in > 1);
-    k_msm_window_combine<F><<<1, 1, 0, st>>>(inR, inA, sh, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
-    B200ZK_CUDA(ctx, cudaGetLastError());
-    return B200ZK_OK;
-}
+#define DECL(SUFFIX)                                                                                                                 \
+    int msm_run_##SUFFIX(Ctx *, const Bases *, size_t, const void *, size_t, const uint8_t *, void *, void *, int);                  \
+    int msm_fixed_base_##SUFFIX(Ctx *, const void *, const void *, size_t, uint32_t, void *, uint8_t *);                             \
+    int msm_into_affine_##SUFFIX(Ctx *, const void *, size_t, void *, uint8_t *);                                                    \
+    int msm_sum_points_##SUFFIX(Ctx *, const void *, size_t, void *);
+DECL(g1)
+DECL(g2)
 
 int msm_run(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density, void *d_out_jac,
             void *d_status_out, int window_bits) {
-    if (bases->group == B200ZK_G1) return msm_run_t<fq_t>(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits);
-    return msm_run_t<fq2_t>(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits);
-}
-
-// ------------------------------------------------------------------------------------------------ fixed-base batch mul
-// table[j][d-1] = d * 2^(8j) * P  (XYZZ), j < nwin, d in 1..255
-template <class F>
-__global__ void k_fixed_base_table(const Affine<F> *__restrict__ base, XYZZ<F> *__restrict__ table, uint32_t nwin) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nwin) return;
-    XYZZ<F> start = XYZZ<F>::from_affine(base[0]);
-    for (uint32_t d = 0; d < 8 * j; d++) start.dbl();
-    XYZZ<F> cur = start;
-    for (uint32_t d = 1; d < 256; d++) {
-        table[(size_t)j * 255 + d - 1] = cur;
-        cur.add(start);
-    }
-}
-template <class F>
-__global__ void __launch_bounds__(128) k_fixed_base_mul(const XYZZ<F> *__restrict__ table, const uint32_t *__restrict__ scalars, size_t n,
-                                                       uint32_t nwin, Affine<F> *__restrict__ out, uint8_t *__restrict__ out_inf) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    XYZZ<F> acc = XYZZ<F>::zero();
-    for (uint32_t j = 0; j < nwin; j++) {
-        uint32_t d = (scalars[8 * i + (j >> 2)] >> (8 * (j & 3))) & 0xff;
-        if (d) acc.add(table[(size_t)j * 255 + d - 1]);
-    }
-    Affine<F> r;
-    bool inf = acc.is_zero();
-    if (inf) { r.x = F::zero(); r.y = F::one(); }
-    else {
-        F inv = (acc.zz * acc.zzz).inverse();
-        r.x = acc.x * (inv * acc.zzz);
-        r.y = acc.y * (inv * acc.zz);
-    }
-    out[i] = r;
-    if (out_inf) out_inf[i] = inf ? 1 : 0;
-}
-template <class F>
-static int msm_fixed_base_t(Ctx *ctx, const void *d_base, const void *d_scalars, size_t n, uint32_t bits, void *d_out, uint8_t *d_out_inf) {
-    if (bits == 0 || bits > 256) return set_error(ctx, B200ZK_ERR_BAD_ARG, "scalar_bits must be in [1, 256]");
-    uint32_t nwin = (bits + 7) / 8;
-    int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, (size_t)nwin * 255 * sizeof(XYZZ<F>));
-    if (rc) return rc;
-    XYZZ<F> *table = (XYZZ<F> *)ctx->scratch2;
-    k_fixed_base_table<F><<<1, 32, 0, ctx->stream>>>((const Affine<F> *)d_base, table, nwin);
-    if (n) k_fixed_base_mul<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(table, (const uint32_t *)d_scalars, n, nwin, (Affine<F> *)d_out, d_out_inf);
-    B200ZK_CUDA(ctx, cudaGetLastError());
-    return B200ZK_OK;
+    if (bases->group == B200ZK_G1) return msm_run_g1(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits);
+    return msm_run_g2(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits);
 }
 int msm_fixed_base(Ctx *ctx, int group, const void *d_base_affine, const void *d_scalars, size_t n, uint32_t scalar_bits, void *d_out_affine,
                    uint8_t *d_out_inf) {
-    if (group == B200ZK_G1) return msm_fixed_base_t<fq_t>(ctx, d_base_affine, d_scalars, n, scalar_bits, d_out_affine, d_out_inf);
-    if (group == B200ZK_G2) return msm_fixed_base_t<fq2_t>(ctx, d_base_affine, d_scalars, n, scalar_bits, d_out_affine, d_out_inf);
+    if (group == B200ZK_G1) return msm_fixed_base_g1(ctx, d_base_affine, d_scalars, n, scalar_bits, d_out_affine, d_out_inf);
+    if (group == B200ZK_G2) return msm_fixed_base_g2(ctx, d_base_affine, d_scalars, n, scalar_bits, d_out_affine, d_out_inf);
     return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
 }
-
-// ------------------------------------------------------------------------------------------------ small helpers
-template <class F>
-__global__ void k_into_affine(const Jacobian<F> *__restrict__ in, size_t n, Affine<F> *__restrict__ out, uint8_t *__restrict__ out_inf) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Affine<F> a;
-    bool ok = jacobian_to_affine(in[i], a);
-    out[i] = a;
-    if (out_inf) out_inf[i] = ok ? 0 : 1;
-}
 int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf) {
-    if (n == 0) return B200ZK_OK;
-    unsigned blocks = (unsigned)((n + 63) / 64);
-    if (group == B200ZK_G1) k_into_affine<fq_t><<<blocks, 64, 0, ctx->stream>>>((const g1_jac_t *)d_jac, n, (g1_affine_t *)d_out_xy, d_out_inf);
-    else if (group == B200ZK_G2) k_into_affine<fq2_t><<<blocks, 64, 0, ctx->stream>>>((const g2_jac_t *)d_jac, n, (g2_affine_t *)d_out_xy, d_out_inf);
-    else return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
-    B200ZK_CUDA(ctx, cudaGetLastError());
-    return B200ZK_OK;
-}
-
-// Sum of n Jacobian points with the reference's add_assign (ec.rs:356-444): strided partials, then a serial fold.
-template <class F>
-__global__ void __launch_bounds__(128) k_sum_points(const Jacobian<F> *__restrict__ in, size_t n, Jacobian<F> *__restrict__ partial, Jacobian<F> *__restrict__ out) {
-    Jacobian<F> acc = Jacobian<F>::zero();
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) jacobian_add(acc, in[i]);
-    partial[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        Jacobian<F> t = Jacobian<F>::zero();
-        for (uint32_t k = 0; k < blockDim.x; k++) jacobian_add(t, partial[k]);
-        *out = t;
-    }
+    if (group == B200ZK_G1) return msm_into_affine_g1(ctx, d_jac, n, d_out_xy, d_out_inf);
+    if (group == B200ZK_G2) return msm_into_affine_g2(ctx, d_jac, n, d_out_xy, d_out_inf);
+    return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
 }
 int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out) {
-    size_t psz = group == B200ZK_G1 ? sizeof(g1_jac_t) : sizeof(g2_jac_t);
-    int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, 128 * psz);
-    if (rc) return rc;
-    if (group == B200ZK_G1) k_sum_points<fq_t><<<1, 128, 0, ctx->stream>>>((const g1_jac_t *)d_jac_in, n, (g1_jac_t *)ctx->scratch2, (g1_jac_t *)d_jac_out);
-    else if (group == B200ZK_G2) k_sum_points<fq2_t><<<1, 128, 0, ctx->stream>>>((const g2_jac_t *)d_jac_in, n, (g2_jac_t *)ctx->scratch2, (g2_jac_t *)d_jac_out);
-    else return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
-    B200ZK_CUDA(ctx, cudaGetLastError());
-    return B200ZK_OK;
+    if (group == B200ZK_G1) return msm_sum_points_g1(ctx, d_jac_in, n, d_jac_out);
+    if (group == B200ZK_G2) return msm_sum_points_g2(ctx, d_jac_in, n, d_jac_out);
+    return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
 }
 
 }  // namespace b200zk
