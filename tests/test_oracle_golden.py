@@ -1,0 +1,243 @@
+"""Pins the CPU oracle (Python + C++ port) against the reference's own golden vectors:
+field KATs, curve KATs, the four tests/*.dat byte-vector files, the test_xordemo pipeline KAT -- and checks
+that the two oracle implementations agree with each other."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cref, domain
+from oracle import multiexp as omx
+from oracle.curve import G1, G2
+from oracle.dummy_engine import DummyEngine
+from oracle.fields import Fq, Fq2, Fr, PrimeField, int_to_limbs, limbs_to_int
+from oracle.groth16 import ONE, Circuit, create_proof, generate_parameters, verify_proof
+from tests import util
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+REF_DAT = "/root/reference/librustzcash/pairing/src/bls12_381/tests"
+
+
+def _h(xs):
+    return [int(x, 16) for x in xs]
+
+
+def test_constants_match_reference():
+    """fr.rs:4-55, fq.rs:5-42: R, R2, INV, S, root of unity re-derived from the moduli."""
+    assert Fr.R == limbs_to_int([0x1fffffffe, 0x5884b7fa00034802, 0x998c4fefecbc4ff5, 0x1824b159acc5056f])
+    assert Fr.R2 == limbs_to_int([0xc999e990f3f29c6d, 0x2b6cedcb87925c23, 0x05d314967254398f, 0x0748d9d99f59ff11])
+    assert Fr.INV == 0xfffffffeffffffff and Fq.INV == 0x89f3fffcfffcfffd
+    assert Fr.to_mont_limbs(Fr.root_of_unity) == [0xb9b58d8c5f0e466a, 0x5b1b4c801819d7ec, 0x0af53ae352a31e64, 0x5bf3adda19e9b27b]
+    assert Fr.to_mont_limbs(7) == [0xefffffff1, 0x17e363d300189c0f, 0xff9c57876f8457b0, 0x351332208fc5a8c4]
+    assert pow(Fr.root_of_unity, 1 << 32, Fr.p) == 1 and pow(Fr.root_of_unity, 1 << 31, Fr.p) != 1
+    assert Fq.R == limbs_to_int([0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745, 0x5c071a97a256ec6d, 0x15f65ec3fa80e493])
+
+
+@pytest.mark.parametrize("name,F", [("fr", Fr), ("fq", Fq)])
+def test_field_kats(name, F):
+    """fr.rs:1240-1262 / fq.rs:2558-2584 (mul on raw Montgomery limbs), fr.rs:1306+ / fq.rs:2630+ (square)."""
+    m = KAT[f"{name}_mul"]
+    assert F.mont_mul_limbs(_h(m["a"]), _h(m["b"])) == _h(m["out"])
+    got = cref.field_vec(name, "mul", np.array([_h(m["a"])], dtype=np.uint64), np.array([_h(m["b"])], dtype=np.uint64))
+    assert [int(x) for x in got[0]] == _h(m["out"])
+    s = KAT[f"{name}_square"]
+    a = _h(s["a"])
+    want = F.to_mont_limbs(limbs_to_int(_h(s["out_repr"])))
+    assert F.mont_mul_limbs(a, a) == want
+    got = cref.field_vec(name, "square", np.array([a], dtype=np.uint64))
+    assert [int(x) for x in got[0]] == want
+
+
+def test_limb_level_mont_mul_equals_modmul():
+    r = util.rng(11)
+    for F, n in ((Fr, 4), (Fq, 6)):
+        a = util.random_field_canonical(r, F.p, 200, n)
+        b = util.random_field_canonical(r, F.p, 200, n)
+        got = cref.field_vec(F.name.lower(), "mul", a, b)
+        for i in range(200):
+            x, y = limbs_to_int(a[i]), limbs_to_int(b[i])
+            want = x * y * F.Rinv % F.p
+            assert limbs_to_int(got[i]) == want
+            assert F.mont_mul_limbs(list(map(int, a[i])), list(map(int, b[i]))) == int_to_limbs(want, n)
+
+
+def test_g1_curve_kats():
+    """ec.rs:1060-1125 (addition), :1128-1175 (doubling): canonical coordinates through from_repr."""
+    k = KAT["g1_add"]
+    p = (limbs_to_int(_h(k["p"][0])), limbs_to_int(_h(k["p"][1])), 1)
+    q = (limbs_to_int(_h(k["q"][0])), limbs_to_int(_h(k["q"][1])), 1)
+    s = G1.into_affine(G1.add(p, q))
+    assert s == (limbs_to_int(_h(k["sum"][0])), limbs_to_int(_h(k["sum"][1])), False)
+    d = KAT["g1_double"]
+    p = (limbs_to_int(_h(d["p"][0])), limbs_to_int(_h(d["p"][1])), 1)
+    assert G1.into_affine(G1.double(p)) == (limbs_to_int(_h(d["dbl"][0])), limbs_to_int(_h(d["dbl"][1])), False)
+    # the C++ port on the same vectors
+    pj = np.array(G1.jacobian_to_limbs(p), dtype=np.uint64)
+    got = cref.point_op("g1", "double", pj)
+    xy, inf = cref.into_affine("g1", got)
+    assert not inf and Fq.from_mont_limbs(xy[:6]) == limbs_to_int(_h(d["dbl"][0]))
+
+
+@pytest.mark.parametrize("name,G,comp", [("g1_uncompressed", G1, False), ("g1_compressed", G1, True),
+                                        ("g2_uncompressed", G2, False), ("g2_compressed", G2, True)])
+def test_dat_vectors(name, G, comp):
+    """pairing/src/bls12_381/tests/mod.rs:55-97: entry i = i * generator, i < 1000, exact bytes.
+    The full files are pinned by sha256 (tests/golden/kat.json); when the reference tree is present the
+    bytes are also compared directly."""
+    meta = KAT["dat"][name]
+    enc = G.encode_compressed if comp else G.encode_uncompressed
+    out = bytearray()
+    p = G.zero()
+    for i in range(1000):
+        b = enc(G.into_affine(p))
+        out += b
+        # decode round trip on a few entries
+        if i < 8:
+            dec = (G.decode_compressed if comp else G.decode_uncompressed)(b)
+            assert dec == G.into_affine(p)
+        p = G.add_mixed(p, G.gen)
+    assert len(out) == meta["entries"] * meta["entry_bytes"]
+    assert [out[i * meta["entry_bytes"]:(i + 1) * meta["entry_bytes"]].hex() for i in range(4)] == meta["first"]
+    assert hashlib.sha256(bytes(out)).hexdigest() == meta["sha256"]
+    path = os.path.join(REF_DAT, f"{name}_valid_test_vectors.dat")
+    if os.path.exists(path):
+        assert open(path, "rb").read() == bytes(out)
+
+
+class XorDemo(Circuit):
+    """groth16/tests/mod.rs:25-96"""
+
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def synthesize(self, cs):
+        a = cs.alloc(lambda: int(self.a))
+        cs.enforce([(ONE, 1), (a, -1)], [(a, 1)], [])
+        b = cs.alloc(lambda: int(self.b))
+        cs.enforce([(ONE, 1), (b, -1)], [(b, 1)], [])
+        c = cs.alloc_input(lambda: int(self.a ^ self.b))
+        cs.enforce([(a, 1), (a, 1)], [(b, 1)], [(a, 1), (b, 1), (c, -1)])
+
+
+def test_xordemo_pipeline_kat():
+    """groth16/tests/mod.rs:98-400: every constant the reference asserts, through generator -> FFT -> multiexp -> proof."""
+    x = KAT["xordemo"]
+    E = DummyEngine
+    F = E.Fr
+    assert F.p == x["modulus"] and F.root_of_unity == x["root_2_10"]
+    assert pow(F.root_of_unity, 1 << 7, F.p) == x["root_2_3"]
+    params, _ = generate_parameters(E, XorDemo(None, None), 1, 1, x["alpha"], x["beta"], x["gamma"], x["delta"], x["tau"])
+    assert len(params.h) == 7 and len(params.l) == 2 and len(params.a) == 4 and len(params.b_g1) == 2 and len(params.b_g2) == 2
+    t_at_tau = (pow(x["tau"], 8, F.p) - 1) % F.p
+    dinv, ginv = F.inv(x["delta"]), F.inv(x["gamma"])
+    for i, h in enumerate(params.h):
+        assert h == pow(x["tau"], i, F.p) * t_at_tau * dinv % F.p
+    assert params.a == x["u_i"]
+    assert params.b_g1 == [v for v in x["v_i"] if v] and params.b_g2 == params.b_g1
+    for i in range(4):
+        t = (x["beta"] * x["u_i"][i] + x["alpha"] * x["v_i"][i] + x["w_i"][i]) % F.p
+        if i < 2:
+            assert params.vk.ic[i] == t * ginv % F.p
+        else:
+            assert params.l[i - 2] == t * dinv % F.p
+    # the H coefficients asserted at mod.rs:384
+    assert domain.h_coefficients(F, [0, 1, 2, 1, 1], [1, 0, 0, 0, 0], [0, 0, 0, 0, 0]) == x["h_coeffs"]
+    r, s = x["r"], x["s_rand"]
+    proof = create_proof(E, XorDemo(True, False), params, r, s)
+    u, v = x["u_i"], x["v_i"]
+    assert proof.a == (x["delta"] * r + x["alpha"] + u[0] + u[1] + u[2]) % F.p
+    assert proof.b == (x["delta"] * s + x["beta"] + v[0] + v[1] + v[2]) % F.p
+    c = (proof.a * s + proof.b * r - x["delta"] * r * s + params.l[0] + sum(params.h[i] * x["h_coeffs"][i] for i in range(7))) % F.p
+    assert proof.c == c
+    assert verify_proof(E, params.vk, proof, [1])
+    assert not verify_proof(E, params.vk, proof, [0])
+
+
+def test_fft_properties_python_oracle():
+    """domain.rs:426-494: compositions are the identity; parallel_fft == serial_fft for every log_cpus."""
+    r = util.rng(12)
+    for log_n in range(0, 8):
+        v = util.rows_to_ints(util.random_fr_repr(r, 1 << log_n))
+        d = domain.EvaluationDomain(Fr, v)
+        d.ifft(); d.fft()
+        assert d.coeffs == v
+        d.icoset_fft(); d.coset_fft()
+        assert d.coeffs == v
+        omega = d.omega
+        for log_cpus in range(0, min(log_n, 3) + 1):
+            a, b = list(v), list(v)
+            domain.serial_fft(Fr, a, omega, log_n)
+            domain.parallel_fft(Fr, b, omega, log_n, log_cpus)
+            assert a == b
+
+
+def test_cpp_fft_matches_python_and_parallel_consistency():
+    r = util.rng(13)
+    for log_n in (0, 1, 3, 6, 9):
+        m = 1 << log_n
+        vals = util.random_fr_mont(r, m)
+        ints = [Fr.from_mont_limbs(x) for x in vals]
+        for kind, name in enumerate(["fft", "ifft", "coset_fft", "icoset_fft"]):
+            d = domain.EvaluationDomain(Fr, ints)
+            getattr(d, name)()
+            for serial in (True, False):
+                got = cref.fft(vals, kind, serial=serial)
+                assert [Fr.from_mont_limbs(x) for x in got] == d.coeffs
+        for log_cpus in range(0, min(log_n, 4) + 1):
+            assert np.array_equal(cref.parallel_fft(vals, log_cpus), cref.fft(vals, 0, serial=True))
+
+
+def test_cpp_multiexp_matches_python_restatement():
+    """C++ port == Python restatement (identical Jacobian triples), == naive sum (multiexp.rs:337-376), errors included."""
+    r = util.rng(14)
+    n = 200
+    xy, ks = util.random_bases("g1", r, n)
+    exps = util.random_fr_repr(r, n)
+    exps[3] = 0
+    exps[4] = (1, 0, 0, 0)
+    pts = [(Fq.from_mont_limbs(p[:6]), Fq.from_mont_limbs(p[6:]), False) for p in xy]
+    ee = util.rows_to_ints(exps)
+    want = omx.multiexp(G1, pts, ee)
+    st, got = cref.multiexp("g1", xy, exps)
+    assert st == 0 and G1.jacobian_from_limbs(list(map(int, got))) == want
+    assert G1.eq(want, omx.naive_multiexp(G1, pts, ee))
+    density = (r.random(n) < 0.5).astype(np.uint8)
+    want = omx.multiexp(G1, pts, ee, density=list(density), base_offset=7)
+    st, got = cref.multiexp("g1", xy, exps, density=density, base_offset=7)
+    assert st == 0 and G1.jacobian_from_limbs(list(map(int, got))) == want
+    # error semantics
+    with pytest.raises(omx.UnexpectedEof):
+        omx.multiexp(G1, pts[:100], ee)
+    assert cref.multiexp("g1", xy[:100], exps)[0] == cref.UNEXPECTED_EOF
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[50] = 1
+    pts2 = list(pts)
+    pts2[50] = G1.affine_zero()
+    with pytest.raises(omx.UnexpectedIdentity):
+        omx.multiexp(G1, pts2, ee)
+    assert cref.multiexp("g1", xy, exps, inf=inf)[0] == cref.UNEXPECTED_IDENTITY
+
+
+def test_g2_multiexp_oracles_agree():
+    r = util.rng(15)
+    n = 40
+    xy, ks = util.random_bases("g2", r, n)
+    exps = util.random_fr_repr(r, n)
+    pts = [(Fq2.from_mont_limbs(list(map(int, p[:12]))), Fq2.from_mont_limbs(list(map(int, p[12:]))), False) for p in xy]
+    want = omx.multiexp(G2, pts, util.rows_to_ints(exps))
+    st, got = cref.multiexp("g2", xy, exps)
+    assert st == 0 and G2.jacobian_from_limbs(list(map(int, got))) == want
+    exp_xy, exp_inf = util.affine_of_scalar("g2", util.expected_scalar(ks, exps))
+    a = G2.into_affine(want)
+    assert np.array_equal(np.array(G2.affine_to_limbs(a), dtype=np.uint64), exp_xy)
+
+
+def test_h_poly_cpp_matches_python():
+    r = util.rng(16)
+    m = 64
+    a, b, c = (util.random_fr_mont(r, m) for _ in range(3))
+    want = domain.h_coefficients(Fr, *[[Fr.from_mont_limbs(x) for x in v] for v in (a, b, c)])
+    got = cref.h_poly(a, b, c)
+    assert [limbs_to_int(x) for x in got] == want

@@ -177,30 +177,19 @@ struct __align__(16) Fp {
     }
     // One row: T += a*bi; T += m*p; T >>= 32 (the shift is implicit: the caller swaps `even` and `odd`).
     // Value represented: T = sum even[k] 2^(32k) + 2^32 * sum odd[k] 2^(32k).
-    // The a*bi products are formed with mul.wide.u32 (IMAD.WIDE, full rate on sm_100a -- measured 18.3 T/s,
-    // same as 32-bit IMAD, while IMAD.HI runs at 0.41x) and added with IADD3.X chains on the ALU pipe; the
-    // m*p products ride mad.lo.cc/madc.hi.cc pairs that ptxas fuses into IMAD.WIDE.U32.X.  Both pipes end up
-    // with ~300 instructions per Fq product (the all-mad.cc form made ptxas emit IMAD + IMAD.HI pairs).
-    __device__ __forceinline__ static void mulwide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
-        unsigned long long t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a), "r"(b));
-        lo = (uint32_t)t; hi = (uint32_t)(t >> 32);
-    }
+    // Written as mad.lo.cc / madc.hi.cc pairs.  Inside the out-of-line product (mul_call) ptxas fuses every pair into
+    // one IMAD.WIDE.U32.X with a predicate carry: ~300 multiplier-pipe instructions + ~80 ALU per Fq product, the
+    // minimum for 32-bit limbs.  (Measured on B200: IMAD.WIDE/.HI issue at 32/clk/SM on the fmaheavy pipe, plain IMAD
+    // at 64/clk/SM; when the same code is inlined into a large kernel ptxas sometimes splits pairs into IMAD +
+    // IMAD.HI + 2 IADD3.X, which is why products go through the call by default.)
     __device__ __forceinline__ static void mad_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *a, uint32_t bi, bool first) {
-        uint32_t pe[N], po[N];
-#pragma unroll
-        for (int j = 0; j < N; j += 2) { mulwide(pe[j], pe[j + 1], a[j], bi); mulwide(po[j], po[j + 1], a[j + 1], bi); }
         if (first) {
-#pragma unroll
-            for (int j = 0; j < N; j++) { even[j] = pe[j]; odd[j] = po[j]; }
+            mul_n(odd, a + 1, bi);
+            mul_n(even, a, bi);
         } else {
-            even[0] = add_cc(even[0], odd[1]);
-#pragma unroll
-            for (int j = 0; j < N - 2; j++) odd[j] = addc_cc(odd[j + 2], po[j]);
-            odd[N - 2] = addc_cc(po[N - 2], 0);
-            odd[N - 1] = addc(po[N - 1], 0);
-            even[0] = add_cc(even[0], pe[0]);
-#pragma unroll
-            for (int j = 1; j < N; j++) even[j] = addc_cc(even[j], pe[j]);
+            even[0] = add_cc(even[0], odd[1]);   // stray limb of the previous row
+            madc_n_rshift(odd, a + 1, bi);       // absorbs that carry (odd[0] is one limb above even[0])
+            cmad_n(even, a, bi);
             odd[N - 1] = addc(odd[N - 1], 0);
         }
         uint32_t mi = even[0] * P::M0;
@@ -208,8 +197,21 @@ struct __align__(16) Fp {
         cmad_mod<0>(even, mi);
         odd[N - 1] = addc(odd[N - 1], 0);
     }
+
     // fq.rs:910-963 mul_assign + fq.rs:1040-1123 mont_reduce  ->  a*b*R^-1 mod p, canonical
     __device__ __forceinline__ friend Fp operator*(const Fp &a, const Fp &b) {
+#ifdef B200ZK_INLINE_MUL
+        return mul_inline(a, b);
+#else
+        return mul_call(a, b);
+#endif
+    }
+    // Out-of-line product: a fully inlined mixed add is ~100 KB of straight-line SASS and ncu showed
+    // `no_instruction` (instruction-cache misses) as the top stall of the bucket-accumulation kernel.  One shared
+    // ~10 KB function body keeps the hot loop inside the instruction cache; arguments and the result travel in
+    // registers (no stack traffic).  -DB200ZK_INLINE_MUL restores inlining for a translation unit.
+    static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
+    __device__ __forceinline__ static Fp mul_inline(const Fp &a, const Fp &b) {
         uint32_t even[N], odd[N];
         // a's limbs interleave: even-indexed at a.v[0], a.v[2].. ; mul_n/cmad_n step by 2 from the pointer given
 #pragma unroll

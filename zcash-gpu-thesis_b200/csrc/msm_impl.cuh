@@ -163,8 +163,11 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ bucket accumulation
+#ifndef B200ZK_ACC_MINBLOCKS
+#define B200ZK_ACC_MINBLOCKS 3
+#endif
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128, B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                        const uint32_t *__restrict__ offsets, uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_buckets) return;

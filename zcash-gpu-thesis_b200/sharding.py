@@ -1,0 +1,30 @@
+"""Multi-GPU partitioning of the prover hot path (one process per GPU).
+
+MSM shards by contiguous base range: rank r of g owns (base, exponent) pairs [lo, hi) of the n pairs, runs the
+full single-GPU multiexp on them and contributes one Jacobian partial (144 B for G1, 288 B for G2); the partials
+are all-gathered (NCCL inside libb200zk.so on the GPU path) and summed in rank order.  Independent NTTs and whole
+proofs go round-robin.  Only plain index arithmetic lives here so that it can be tested on CPU (gloo)."""
+from __future__ import annotations
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced split of n pairs: the first n % world ranks get one extra pair."""
+    assert 0 <= rank < world
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def shard_density(density, lo: int, hi: int, base_offset: int = 0):
+    """For a density-mapped multiexp the base cursor of a shard starts after the set bits that precede it
+    (multiexp.rs:174-196 consumes one base per set bit).  Returns (density[lo:hi], base_offset + popcount(density[:lo]))."""
+    if density is None:
+        return None, base_offset + lo
+    before = int(sum(1 for b in density[:lo] if b))
+    return density[lo:hi], base_offset + before
+
+
+def round_robin(items: int, rank: int, world: int):
+    """Indices of the independent work items (the a/b/c NTTs of a proof, or whole proofs of a batch) for this rank."""
+    return list(range(rank, items, world))
