@@ -59,6 +59,7 @@ enum { B200ZK_POINT_DOUBLE = 0, B200ZK_POINT_ADD = 1, B200ZK_POINT_ADD_MIXED = 2
 
 typedef struct b200zk_ctx b200zk_ctx;
 typedef struct b200zk_bases b200zk_bases;
+typedef struct b200zk_crs b200zk_crs;
 
 /* ---- context ------------------------------------------------------------------------------------------------- */
 /* Replaces Worker::new() (bellman/src/multicore.rs:24-31): a context owns one CUDA stream on `device`. */
@@ -151,6 +152,25 @@ int b200zk_point_op(b200zk_ctx *ctx, int group, int op, const uint64_t *a, const
  * (the `into_repr` exponents of the H multiexp).  a, b, c are clobbered in the _dev form. */
 int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_m, uint64_t *out);
 int b200zk_h_poly_dev(b200zk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_m, void *d_out);
+
+/* ---- groth16::create_proof (bellman/src/groth16/prover.rs:205-364), everything after circuit synthesis --------------- */
+/* A proving key resident in HBM: the five query vectors of `Parameters` (groth16/mod.rs:215-238) as bases handles
+ * (h, l, a, b_g1, b_g2; "never contains points at infinity") plus the VerifyingKey elements the prover touches
+ * (vk.alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2: affine x||y Montgomery; vk_infinity[5] flags or NULL).
+ * Window tables for delta_g1 / delta_g2 are built once here.  The handles must outlive the CRS object. */
+int b200zk_crs_create(b200zk_ctx *ctx, const b200zk_bases *h, const b200zk_bases *l, const b200zk_bases *a, const b200zk_bases *b_g1,
+                      const b200zk_bases *b_g2, const uint64_t alpha_g1[12], const uint64_t beta_g1[12], const uint64_t beta_g2[24],
+                      const uint64_t delta_g1[12], const uint64_t delta_g2[24], const uint8_t *vk_infinity, b200zk_crs **out);
+void b200zk_crs_free(b200zk_crs *crs);
+/* create_proof for an already synthesized ProvingAssignment (prover.rs:84-190): a, b, c = the evaluation vectors
+ * (n_constraints x 4 u64 Montgomery, including the `x * 0 = 0` input rows of prover.rs:228-234); inputs / aux = the
+ * assignments as canonical FrRepr (prover.rs:290-291); the three density maps as bytes; r, s canonical FrRepr.
+ * Outputs: proof.a (G1 affine x||y), proof.b (G2 affine), proof.c (G1 affine), Montgomery limbs, + 3 infinity flags.
+ * Errors as the reference: UNEXPECTED_IDENTITY (subversion check / identity base), UNEXPECTED_EOF, DEGREE_TOO_LARGE. */
+int b200zk_groth16_prove(b200zk_ctx *ctx, const b200zk_crs *crs, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_constraints,
+                         const uint64_t *inputs, size_t n_inputs, const uint64_t *aux, size_t n_aux, const uint8_t *a_aux_density,
+                         const uint8_t *b_input_density, const uint8_t *b_aux_density, const uint64_t r[4], const uint64_t s[4],
+                         uint64_t proof_a[12], uint64_t proof_b[24], uint64_t proof_c[12], uint8_t inf_flags[3]);
 
 /* Per-kernel timing for the roofline report: when enabled, b200zk_multiexp(_dev) brackets its dominant kernel
  * (bucket accumulation) with CUDA events on the context's stream; read() synchronises and returns the summed

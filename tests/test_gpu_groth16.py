@@ -1,0 +1,131 @@
+"""groth16::create_proof on the GPU vs the oracle: identical proof points and identical 192 proof bytes for fixed (r, s)
+(groth16/mod.rs:493-575 and bellman/tests/mimc.rs re-targeted; the CRS comes from the oracle's generate_parameters)."""
+import numpy as np
+import pytest
+
+from oracle.curve import G1, G2
+from oracle.fields import Fq, Fq2, Fr, int_to_limbs
+from oracle.groth16 import ONE, Circuit, generate_parameters, proof_bytes, prove_from_assignment, synthesize_assignment
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+class BlsEngine:
+    Fr = Fr
+    G1 = G1
+    G2 = G2
+
+
+class MiMCLike(Circuit):
+    """A small MiMC-style circuit (bellman/tests/mimc.rs:86-167): x_{i+1} = (x_i + k + c_i)^3 + y_i, swapped each round."""
+
+    def __init__(self, xl, xr, constants):
+        self.xl, self.xr, self.constants = xl, xr, constants
+
+    def synthesize(self, cs):
+        p = Fr.p
+        xl_v, xr_v = self.xl, self.xr
+        xl = cs.alloc(lambda: xl_v)
+        xr = cs.alloc(lambda: xr_v)
+        n = len(self.constants)
+        for i, c in enumerate(self.constants):
+            t = (xl_v + c) % p
+            tmp_v = t * t % p
+            tmp = cs.alloc(lambda v=tmp_v: v)
+            cs.enforce([(xl, 1), (ONE, c)], [(xl, 1), (ONE, c)], [(tmp, 1)])
+            new_v = (tmp_v * t + xr_v) % p
+            if i == n - 1:
+                new = cs.alloc_input(lambda v=new_v: v)
+            else:
+                new = cs.alloc(lambda v=new_v: v)
+            cs.enforce([(tmp, 1)], [(xl, 1), (ONE, c)], [(new, 1), (xr, -1)])
+            xr, xr_v = xl, xl_v
+            xl, xl_v = new, new_v
+
+
+class Silly(Circuit):
+    """groth16/mod.rs:493-535 MySillyCircuit: a * b = c with c public."""
+
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def synthesize(self, cs):
+        a = cs.alloc(lambda: self.a)
+        b = cs.alloc(lambda: self.b)
+        c = cs.alloc_input(lambda: self.a * self.b % Fr.p)
+        cs.enforce([(a, 1)], [(b, 1)], [(c, 1)])
+
+
+def _aff_limbs(G, p):
+    return np.array(G.affine_to_limbs(p), dtype=np.uint64)
+
+
+def _upload(worker, params):
+    import zcash_gpu_thesis_b200 as zk
+
+    pack = lambda G, v: np.array([G.affine_to_limbs(p) for p in v], dtype=np.uint64).reshape(len(v), -1)
+    vk = params.vk
+    return zk.Parameters(worker, pack(G1, params.h), pack(G1, params.l), pack(G1, params.a), pack(G1, params.b_g1), pack(G2, params.b_g2),
+                         _aff_limbs(G1, vk.alpha_g1), _aff_limbs(G1, vk.beta_g1), _aff_limbs(G2, vk.beta_g2), _aff_limbs(G1, vk.delta_g1),
+                         _aff_limbs(G2, vk.delta_g2))
+
+
+def _gpu_prove(worker, dev_params, asg, r, s):
+    import zcash_gpu_thesis_b200 as zk
+
+    mont = lambda v: np.array([Fr.to_mont_limbs(x) for x in v], dtype=np.uint64).reshape(len(v), 4)
+    rep = lambda v: np.array([int_to_limbs(x, 4) for x in v], dtype=np.uint64).reshape(len(v), 4)
+    return zk.create_proof_from_assignment(worker, dev_params, mont(asg.a), mont(asg.b), mont(asg.c), rep(asg.input_assignment),
+                                           rep(asg.aux_assignment), asg.a_aux_density, asg.b_input_density, asg.b_aux_density, r, s)
+
+
+def _same_point(G, limbs, inf, want):
+    if want[2]:
+        return bool(inf)
+    return (not inf) and list(map(int, limbs)) == G.affine_to_limbs(want)
+
+
+@pytest.mark.parametrize("which", ["silly", "mimc"])
+def test_create_proof_matches_oracle(worker, which):
+    E = BlsEngine
+    r0 = util.rng(2000)
+    rnd = lambda: util.rows_to_ints(util.random_fr_repr(r0, 1))[0]
+    if which == "silly":
+        blank, circ = Silly(0, 0), Silly(rnd(), rnd())
+    else:
+        consts = [rnd() for _ in range(24)]
+        blank, circ = MiMCLike(0, 0, consts), MiMCLike(rnd(), rnd(), consts)
+    toxic = [rnd() for _ in range(5)]
+    params, _ = generate_parameters(E, blank, G1.gen, G2.gen, *toxic)
+    dev = _upload(worker, params)
+    for trial in range(2):
+        r, s = rnd(), rnd()
+        asg = synthesize_assignment(E, circ)
+        want = prove_from_assignment(E, asg, params, r, s)
+        got = _gpu_prove(worker, dev, asg, r, s)
+        assert _same_point(G1, got.a, got.inf[0], want.a)
+        assert _same_point(G2, got.b, got.inf[1], want.b)
+        assert _same_point(G1, got.c, got.inf[2], want.c)
+        assert got.write(worker) == proof_bytes(want)
+        assert len(got.write(worker)) == 192  # groth16/mod.rs:567
+    # the proof satisfies the Groth16 equation in the exponent (toxic waste known): A*B = alpha*beta + acc*gamma + C*delta
+    alpha, beta, gamma, delta, tau = toxic
+    # recover discrete logs through the oracle pipeline on the DummyEngine-like scalar model is not possible for BLS points;
+    # the pairing-free consistency check is the equality with the oracle proof above plus the oracle's own xordemo KAT.
+
+
+def test_subversion_check(worker):
+    """prover.rs:320-324: delta at infinity -> UnexpectedIdentity."""
+    import zcash_gpu_thesis_b200 as zk
+
+    E = BlsEngine
+    params, _ = generate_parameters(E, Silly(0, 0), G1.gen, G2.gen, 3, 5, 7, 11, 13)
+    pack = lambda G, v: np.array([G.affine_to_limbs(p) for p in v], dtype=np.uint64).reshape(len(v), -1)
+    vk = params.vk
+    dev = zk.Parameters(worker, pack(G1, params.h), pack(G1, params.l), pack(G1, params.a), pack(G1, params.b_g1), pack(G2, params.b_g2),
+                        _aff_limbs(G1, vk.alpha_g1), _aff_limbs(G1, vk.beta_g1), _aff_limbs(G2, vk.beta_g2), _aff_limbs(G1, vk.delta_g1),
+                        _aff_limbs(G2, vk.delta_g2), vk_infinity=[0, 0, 0, 1, 0])
+    asg = synthesize_assignment(E, Silly(2, 3))
+    with pytest.raises(zk.UnexpectedIdentity):
+        _gpu_prove(worker, dev, asg, 5, 6)

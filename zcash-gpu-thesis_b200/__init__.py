@@ -18,7 +18,10 @@ from .bellman import (  # noqa: F401
     PolynomialDegreeTooLarge,
     SynthesisError,
     UnexpectedIdentity,
+    Parameters,
+    Proof,
     Worker,
+    create_proof_from_assignment,
     field_vec,
     fixed_base_mul,
     h_poly,

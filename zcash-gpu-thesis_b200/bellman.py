@@ -461,3 +461,91 @@ def fixed_base_mul(worker, group, base_xy, scalars, scalar_bits=255):
     worker.sync()
     ds.free()
     return dout, dinf, n
+
+
+# ------------------------------------------------------------------------------------------------------ groth16
+FQ_MODULUS = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+
+
+class Parameters:
+    """groth16::Parameters (groth16/mod.rs:215-238) resident in HBM: the h, l, a, b_g1, b_g2 query vectors as `Bases`
+    and the VerifyingKey elements the prover reads.  Acts as the ParameterSource of create_proof."""
+
+    def __init__(self, worker, h, l, a, b_g1, b_g2, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, vk_infinity=None):
+        self.worker = worker
+        mk = lambda g, v: v if isinstance(v, Bases) else Bases(worker, g, v)
+        self.h, self.l, self.a, self.b_g1 = (mk(L.G1, v) for v in (h, l, a, b_g1))
+        self.b_g2 = mk(L.G2, b_g2)
+        vk = [_u64(v) for v in (alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2)]
+        inf = None if vk_infinity is None else np.ascontiguousarray(vk_infinity, dtype=np.uint8)
+        hnd = C.c_void_p()
+        st = worker.lib.b200zk_crs_create(worker.ctx, self.h.handle, self.l.handle, self.a.handle, self.b_g1.handle, self.b_g2.handle,
+                                          _ptr(vk[0]), _ptr(vk[1]), _ptr(vk[2]), _ptr(vk[3]), _ptr(vk[4]), _ptr(inf), C.byref(hnd))
+        if st:
+            _raise(worker, st)
+        self.handle = hnd
+
+    def free(self):
+        if getattr(self, "handle", None) is not None and self.worker.ctx is not None:
+            self.worker.lib.b200zk_crs_free(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Proof:
+    """groth16::Proof (groth16/mod.rs:27-53): affine a (G1), b (G2), c (G1) as Montgomery limbs + infinity flags."""
+
+    def __init__(self, a, b, c, inf):
+        self.a, self.b, self.c, self.inf = a, b, c, [bool(x) for x in inf]
+
+    def write(self, worker) -> bytes:
+        """Proof::write: 48 + 96 + 48 compressed big-endian bytes (ec.rs:839-868, 2801-2830)."""
+        coords = np.concatenate([self.a, self.b, self.c]).reshape(-1, 6)
+        canon = field_vec(worker, L.FQ, L.OP_INTO_REPR, coords)  # Montgomery -> canonical on the device
+        ints = [sum(int(v) << (64 * i) for i, v in enumerate(row)) for row in canon]
+        ax, ay, bx0, bx1, by0, by1, cx, cy = ints
+
+        def g1(x, y, inf):
+            if inf:
+                return bytes([0xC0]) + bytes(47)
+            out = bytearray(x.to_bytes(48, "big"))
+            out[0] |= 0x80 | (0x20 if y > (FQ_MODULUS - y) % FQ_MODULUS else 0)
+            return bytes(out)
+
+        def g2(x0, x1, y0, y1, inf):
+            if inf:
+                return bytes([0xC0]) + bytes(95)
+            out = bytearray(x1.to_bytes(48, "big") + x0.to_bytes(48, "big"))  # c1 then c0
+            ny0, ny1 = (FQ_MODULUS - y0) % FQ_MODULUS, (FQ_MODULUS - y1) % FQ_MODULUS
+            out[0] |= 0x80 | (0x20 if (y1, y0) > (ny1, ny0) else 0)
+            return bytes(out)
+
+        return g1(ax, ay, self.inf[0]) + g2(bx0, bx1, by0, by1, self.inf[1]) + g1(cx, cy, self.inf[2])
+
+
+def create_proof_from_assignment(worker, params: Parameters, a, b, c, input_assignment, aux_assignment, a_aux_density, b_input_density,
+                                 b_aux_density, r, s) -> Proof:
+    """groth16::create_proof (prover.rs:205-364) after circuit synthesis: a, b, c = ProvingAssignment's evaluation vectors
+    ((n, 4) Montgomery), input/aux assignments as canonical FrRepr ((n, 4)), densities as DensityTracker or byte arrays,
+    r, s as Python ints (E::Fr)."""
+    a, b, c = _u64(a, 4), _u64(b, 4), _u64(c, 4)
+    inputs, aux = _u64(input_assignment, 4), _u64(aux_assignment, 4)
+    dens = []
+    for d in (a_aux_density, b_input_density, b_aux_density):
+        dens.append(d.as_bytes() if isinstance(d, DensityTracker) else np.ascontiguousarray(d, dtype=np.uint8))
+    assert dens[0].shape[0] == aux.shape[0] and dens[1].shape[0] == inputs.shape[0] and dens[2].shape[0] == aux.shape[0]
+    rl = np.array([(r >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    sl = np.array([(s >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    pa, pb, pc = np.zeros(12, np.uint64), np.zeros(24, np.uint64), np.zeros(12, np.uint64)
+    inf = np.zeros(3, np.uint8)
+    st = worker.lib.b200zk_groth16_prove(worker.ctx, params.handle, _ptr(a), _ptr(b), _ptr(c), a.shape[0], _ptr(inputs), inputs.shape[0],
+                                         _ptr(aux), aux.shape[0], _ptr(dens[0]), _ptr(dens[1]), _ptr(dens[2]), _ptr(rl), _ptr(sl),
+                                         _ptr(pa), _ptr(pb), _ptr(pc), _ptr(inf))
+    if st:
+        _raise(worker, st)
+    return Proof(pa, pb, pc, inf)

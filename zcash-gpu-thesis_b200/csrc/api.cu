@@ -71,6 +71,7 @@ using namespace b200zk;
 
 struct b200zk_ctx : public Ctx {};
 struct b200zk_bases : public Bases {};
+struct b200zk_crs : public Crs {};
 
 #define CHECK_CTX(ctx) do { if (!(ctx)) return B200ZK_ERR_BAD_ARG; } while (0)
 #define USE_DEVICE(ctx) B200ZK_CUDA(ctx, cudaSetDevice((ctx)->device))
@@ -112,6 +113,7 @@ void b200zk_destroy(b200zk_ctx *ctx) {
     cudaFree(ctx->small_slot);
     cudaFree(ctx->scratch);
     cudaFree(ctx->scratch2);
+    cudaFree(ctx->scratch3);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -485,6 +487,68 @@ int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const u
     if (bytes > 32) B200ZK_CUDA(ctx, cudaMemcpyAsync(out, s + 3 * bytes, bytes - 32, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- groth16
+int b200zk_crs_create(b200zk_ctx *ctx, const b200zk_bases *h, const b200zk_bases *l, const b200zk_bases *a, const b200zk_bases *b_g1,
+                      const b200zk_bases *b_g2, const uint64_t alpha_g1[12], const uint64_t beta_g1[12], const uint64_t beta_g2[24],
+                      const uint64_t delta_g1[12], const uint64_t delta_g2[24], const uint8_t *vk_infinity, b200zk_crs **out) {
+    CHECK_CTX(ctx);
+    if (!out || !h || !l || !a || !b_g1 || !b_g2) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    if (h->group != B200ZK_G1 || l->group != B200ZK_G1 || a->group != B200ZK_G1 || b_g1->group != B200ZK_G1 || b_g2->group != B200ZK_G2)
+        return set_error(ctx, B200ZK_ERR_BAD_ARG, "query vector in the wrong group");
+    USE_DEVICE(ctx);
+    b200zk_crs *c = new b200zk_crs();
+    c->ctx = ctx;
+    c->h = const_cast<b200zk_bases *>(h); c->l = const_cast<b200zk_bases *>(l); c->a = const_cast<b200zk_bases *>(a);
+    c->b_g1 = const_cast<b200zk_bases *>(b_g1); c->b_g2 = const_cast<b200zk_bases *>(b_g2);
+    c->vk = c->table_delta_g1 = c->table_delta_g2 = nullptr;
+    c->subverted = vk_infinity && (vk_infinity[3] || vk_infinity[4]);
+    const size_t t1 = (size_t)32 * 255 * 192, t2 = (size_t)32 * 255 * 384;
+    if (cudaMalloc(&c->vk, 3 * 96 + 2 * 192) != cudaSuccess || cudaMalloc(&c->table_delta_g1, t1) != cudaSuccess ||
+        cudaMalloc(&c->table_delta_g2, t2) != cudaSuccess) {
+        b200zk_crs_free(c);
+        return set_error(ctx, B200ZK_ERR_CUDA, "cudaMalloc(crs) failed");
+    }
+    char *v = (char *)c->vk;
+    cudaMemcpyAsync(v, alpha_g1, 96, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(v + 96, beta_g1, 96, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(v + 192, delta_g1, 96, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(v + 288, beta_g2, 192, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(v + 480, delta_g2, 192, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = B200ZK_OK;
+    if (!c->subverted) {
+        rc = msm_build_table(ctx, B200ZK_G1, v + 192, c->table_delta_g1, 32);
+        if (!rc) rc = msm_build_table(ctx, B200ZK_G2, v + 480, c->table_delta_g2, 32);
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_error(ctx, B200ZK_ERR_CUDA, "crs upload failed");
+    if (rc) { b200zk_crs_free(c); return rc; }
+    *out = c;
+    return B200ZK_OK;
+}
+
+void b200zk_crs_free(b200zk_crs *crs) {
+    if (!crs) return;
+    cudaSetDevice(crs->ctx->device);
+    cudaStreamSynchronize(crs->ctx->stream);
+    cudaFree(crs->vk);
+    cudaFree(crs->table_delta_g1);
+    cudaFree(crs->table_delta_g2);
+    delete crs;
+}
+
+int b200zk_groth16_prove(b200zk_ctx *ctx, const b200zk_crs *crs, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_constraints,
+                         const uint64_t *inputs, size_t n_inputs, const uint64_t *aux, size_t n_aux, const uint8_t *a_aux_density,
+                         const uint8_t *b_input_density, const uint8_t *b_aux_density, const uint64_t r[4], const uint64_t s[4],
+                         uint64_t proof_a[12], uint64_t proof_b[24], uint64_t proof_c[12], uint8_t inf_flags[3]) {
+    CHECK_CTX(ctx);
+    if (!crs || !a || !b || !c || !inputs || (n_aux && !aux) || !a_aux_density && n_aux || !b_input_density || (n_aux && !b_aux_density) || !r || !s ||
+        !proof_a || !proof_b || !proof_c)
+        return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    if (crs->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "CRS lives on another device");
+    USE_DEVICE(ctx);
+    ProveArgs g{a, b, c, n_constraints, inputs, n_inputs, aux, n_aux, a_aux_density, b_input_density, b_aux_density, r, s};
+    return groth16_prove(ctx, crs, g, proof_a, proof_b, proof_c, inf_flags);
 }
 
 int b200zk_profile_enable(b200zk_ctx *ctx, int on) {

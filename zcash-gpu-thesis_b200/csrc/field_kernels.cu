@@ -105,7 +105,10 @@ __global__ void k_microbench(int iters, uint32_t seed, uint32_t *out) {
 #pragma unroll
             for (int u = 0; u < 8; u++)
 #pragma unroll
-                for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(m), "r"(y[i]));
+                for (int i = 0; i < 8; i++) {  // the multiplicand depends on the previous result: nothing is loop invariant
+                    uint32_t lo = (uint32_t)w[i];
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(lo), "r"(m));
+                }
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) x[i] = (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32);

@@ -1,0 +1,207 @@
+// The numeric pipeline of groth16::create_proof (bellman/src/groth16/prover.rs:249-364) on the device:
+// H polynomial (7 NTTs + pointwise, prover.rs:256-287) -> 8 multiexps (prover.rs:289-318) -> proof assembly
+// (prover.rs:326-363).  Circuit synthesis (prover.rs:212-234) stays on the host: the caller passes the a/b/c
+// evaluation vectors, the input / aux assignments and the three density maps that ProvingAssignment collects.
+//
+// Assembly identities (same group elements as prover.rs:326-354, fewer scalar multiplications):
+//   g_a = r*delta_g1 + alpha_g1 + (a_inputs + a_aux)
+//   g_b = s*delta_g2 + beta_g2  + (b2_inputs + b2_aux)
+//   g_c = s*g_a + r*(beta_g1 + b1_inputs + b1_aux) + h + l
+//        [ = rs*delta_g1 + s*alpha_g1 + r*beta_g1 + s*a_answer + r*b1_answer + h + l ]
+// r*delta_g1 and s*delta_g2 use per-CRS window tables (32 windows x 255 multiples, built once at upload, summed by a
+// warp tree); the two variable-base products are MSB-first double-and-add with the reference's Jacobian formulas.
+#include "ec.cuh"
+#include "internal.h"
+
+namespace b200zk {
+
+enum { R_H = 0, R_L, R_A_IN, R_A_AUX, R_B1_IN, R_B1_AUX, R_COUNT_G1 };  // G1 multiexp results (Jacobian, 144 B each)
+enum { R_B2_IN = 0, R_B2_AUX, R_COUNT_G2 };                             // G2 results (288 B each)
+
+// scal[0] = r, scal[1] = s  (canonical FrRepr, 8 u32 each)
+// block 0: T = r * delta_g1 (table), g_a = T + alpha_g1 + a_in + a_aux ; B1 = beta_g1 + b1_in + b1_aux
+// block 1: T = s * delta_g2 (table), g_b = T + beta_g2 + b2_in + b2_aux  -> affine
+template <class F>
+__device__ void table_mul_warp(const XYZZ<F> *table, const uint32_t *scalar, XYZZ<F> *sm, XYZZ<F> &out) {
+    const uint32_t j = threadIdx.x;  // 32 threads, one 8-bit window each
+    uint32_t d = (scalar[j >> 2] >> (8 * (j & 3))) & 0xff;
+    sm[j] = d ? table[(size_t)j * 255 + d - 1] : XYZZ<F>::zero();
+    __syncthreads();
+    for (uint32_t stride = 16; stride > 0; stride >>= 1) {
+        if (j < stride) {
+            XYZZ<F> t = sm[j];
+            t.add(sm[j + stride]);
+            sm[j] = t;
+        }
+        __syncthreads();
+    }
+    out = sm[0];
+}
+
+__global__ void __launch_bounds__(32) k_proof_stage1(const g1_xyzz_t *table_d1, const g2_xyzz_t *table_d2, const uint32_t *scal,
+                                                    const g1_affine_t *vk_g1 /* alpha, beta, delta */, const g2_affine_t *vk_g2 /* beta, delta */,
+                                                    const g1_jac_t *res_g1, const g2_jac_t *res_g2, g1_jac_t *out_g1 /* g_a, B1 */,
+                                                    g2_affine_t *proof_b, uint8_t *inf_flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (blockIdx.x == 0) {
+        g1_xyzz_t *sm = reinterpret_cast<g1_xyzz_t *>(smem_raw);
+        g1_xyzz_t t;
+        table_mul_warp<fq_t>(table_d1, scal, sm, t);
+        if (threadIdx.x == 0) {
+            t.add_mixed(vk_g1[0], false);
+            t.add(g1_xyzz_t::from_jacobian(res_g1[R_A_IN]));
+            t.add(g1_xyzz_t::from_jacobian(res_g1[R_A_AUX]));
+            out_g1[0] = t.to_jacobian();
+            g1_xyzz_t b1 = g1_xyzz_t::from_affine(vk_g1[1]);
+            b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1_IN]));
+            b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1_AUX]));
+            out_g1[1] = b1.to_jacobian();
+        }
+    } else {
+        g2_xyzz_t *sm = reinterpret_cast<g2_xyzz_t *>(smem_raw);
+        g2_xyzz_t t;
+        table_mul_warp<fq2_t>(table_d2, scal + 8, sm, t);
+        if (threadIdx.x == 0) {
+            t.add_mixed(vk_g2[0], false);
+            t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2_IN]));
+            t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2_AUX]));
+            g2_affine_t a;
+            bool ok = jacobian_to_affine(t.to_jacobian(), a);
+            *proof_b = a;
+            inf_flags[1] = ok ? 0 : 1;
+        }
+    }
+}
+
+// out[b] = scal_sel[b] * in[b]  (CurveProjective::mul_assign, ec.rs:528-552: MSB-first double and add), b = blockIdx.x in {0, 1}:
+// block 0: s * g_a, block 1: r * B1
+__global__ void k_proof_stage2(const g1_jac_t *in, const uint32_t *scal, g1_jac_t *out) {
+    if (threadIdx.x != 0) return;
+    const uint32_t b = blockIdx.x;
+    const uint32_t *k = scal + (b == 0 ? 8 : 0);
+    g1_jac_t p = in[b];
+    g1_jac_t acc = g1_jac_t::zero();
+    bool found = false;
+    for (int i = 255; i >= 0; i--) {
+        bool bit = (k[i >> 5] >> (i & 31)) & 1;
+        if (found) jacobian_double(acc); else found = bit;
+        if (bit) jacobian_add(acc, p);
+    }
+    out[b] = acc;
+}
+
+// block 0: proof.a = affine(g_a); block 1: proof.c = affine(s*g_a + r*B1 + h + l)
+__global__ void k_proof_stage3(const g1_jac_t *ga_b1, const g1_jac_t *prods, const g1_jac_t *res_g1, g1_affine_t *proof_a, g1_affine_t *proof_c,
+                               uint8_t *inf_flags) {
+    if (threadIdx.x != 0) return;
+    if (blockIdx.x == 0) {
+        g1_affine_t a;
+        bool ok = jacobian_to_affine(ga_b1[0], a);
+        *proof_a = a;
+        inf_flags[0] = ok ? 0 : 1;
+    } else {
+        g1_jac_t c = prods[0];
+        jacobian_add(c, prods[1]);
+        jacobian_add(c, res_g1[R_H]);
+        jacobian_add(c, res_g1[R_L]);
+        g1_affine_t a;
+        bool ok = jacobian_to_affine(c, a);
+        *proof_c = a;
+        inf_flags[2] = ok ? 0 : 1;
+    }
+}
+
+static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c, uint8_t *inf_flags) {
+    cudaStream_t st = ctx->stream;
+    if (crs->subverted) return set_error(ctx, B200ZK_ERR_UNEXPECTED_IDENTITY, "delta_g1 / delta_g2 is the identity (subversion check, prover.rs:320-324)");
+    // EvaluationDomain::from_coeffs (domain.rs:48-81)
+    size_t m = 1;
+    uint32_t log_m = 0;
+    while (m < g.n_constraints) {
+        m *= 2;
+        log_m++;
+        if (log_m >= 32) return set_error(ctx, B200ZK_ERR_DEGREE_TOO_LARGE, "PolynomialDegreeTooLarge");
+    }
+    const size_t vec = m * 32;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+    size_t o_a = take(vec), o_b = take(vec), o_c = take(vec), o_h = take(vec);
+    size_t o_in = take(g.n_inputs * 32), o_aux = take(g.n_aux * 32);
+    size_t o_da = take(g.n_aux), o_dbi = take(g.n_inputs), o_dba = take(g.n_aux);
+    size_t o_scal = take(64), o_r1 = take(R_COUNT_G1 * 144), o_r2 = take(R_COUNT_G2 * 288), o_st = take(8 * 4);
+    size_t o_mid = take(2 * 144), o_prod = take(2 * 144), o_pa = take(96), o_pb = take(192), o_pc = take(96), o_inf = take(4);
+    int rc = ensure_scratch(ctx, &ctx->scratch3, &ctx->scratch3_bytes, off);
+    if (rc) return rc;
+    char *w = (char *)ctx->scratch3;
+    // ---- inputs to HBM (zero padding of a, b, c up to m as from_coeffs does)
+    auto up = [&](size_t o, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(w + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+    const size_t used = g.n_constraints * 32;
+    B200ZK_CUDA(ctx, up(o_a, g.a, used));
+    B200ZK_CUDA(ctx, up(o_b, g.b, used));
+    B200ZK_CUDA(ctx, up(o_c, g.c, used));
+    if (vec > used) {
+        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_a + used, 0, vec - used, st));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_b + used, 0, vec - used, st));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_c + used, 0, vec - used, st));
+    }
+    B200ZK_CUDA(ctx, up(o_in, g.inputs, g.n_inputs * 32));
+    B200ZK_CUDA(ctx, up(o_aux, g.aux, g.n_aux * 32));
+    B200ZK_CUDA(ctx, up(o_da, g.a_aux_density, g.n_aux));
+    B200ZK_CUDA(ctx, up(o_dbi, g.b_input_density, g.n_inputs));
+    B200ZK_CUDA(ctx, up(o_dba, g.b_aux_density, g.n_aux));
+    B200ZK_CUDA(ctx, up(o_scal, g.r, 32));
+    B200ZK_CUDA(ctx, up(o_scal + 32, g.s, 32));
+    // b_input_density_total decides where the aux cursor of the B queries starts (prover.rs:305-315)
+    size_t b_in_total = 0;
+    for (size_t i = 0; i < g.n_inputs; i++) b_in_total += g.b_input_density[i] ? 1 : 0;
+
+    // ---- H polynomial (prover.rs:256-287)
+    if ((rc = ntt_h_poly(ctx, w + o_a, w + o_b, w + o_c, log_m, w + o_h))) return rc;
+    // ---- the 8 multiexps (prover.rs:289-318)
+    g1_jac_t *r1 = (g1_jac_t *)(w + o_r1);
+    g2_jac_t *r2 = (g2_jac_t *)(w + o_r2);
+    uint32_t *stw = (uint32_t *)(w + o_st);
+    const uint8_t *da = (const uint8_t *)(w + o_da), *dbi = (const uint8_t *)(w + o_dbi), *dba = (const uint8_t *)(w + o_dba);
+    struct Job { const Bases *b; size_t off; size_t src; size_t n; const uint8_t *d; void *out; };
+    Job jobs[8] = {
+        {crs->h, 0, o_h, m - 1, nullptr, &r1[R_H]},
+        {crs->l, 0, o_aux, g.n_aux, nullptr, &r1[R_L]},
+        {crs->a, 0, o_in, g.n_inputs, nullptr, &r1[R_A_IN]},
+        {crs->a, g.n_inputs, o_aux, g.n_aux, da, &r1[R_A_AUX]},
+        {crs->b_g1, 0, o_in, g.n_inputs, dbi, &r1[R_B1_IN]},
+        {crs->b_g1, b_in_total, o_aux, g.n_aux, dba, &r1[R_B1_AUX]},
+        {crs->b_g2, 0, o_in, g.n_inputs, dbi, &r2[R_B2_IN]},
+        {crs->b_g2, b_in_total, o_aux, g.n_aux, dba, &r2[R_B2_AUX]},
+    };
+    for (int j = 0; j < 8; j++) {
+        if ((rc = msm_run(ctx, jobs[j].b, jobs[j].off, w + jobs[j].src, jobs[j].n, jobs[j].d, jobs[j].out, stw + j, 0))) return rc;
+    }
+    // ---- assembly (prover.rs:326-363)
+    const g1_affine_t *vk1 = (const g1_affine_t *)crs->vk;
+    const g2_affine_t *vk2 = (const g2_affine_t *)((const char *)crs->vk + 3 * 96);
+    g1_jac_t *mid = (g1_jac_t *)(w + o_mid), *prod = (g1_jac_t *)(w + o_prod);
+    uint8_t *dinf = (uint8_t *)(w + o_inf);
+    k_proof_stage1<<<2, 32, 32 * sizeof(g2_xyzz_t), st>>>((const g1_xyzz_t *)crs->table_delta_g1, (const g2_xyzz_t *)crs->table_delta_g2,
+                                                         (const uint32_t *)(w + o_scal), vk1, vk2, r1, r2, mid, (g2_affine_t *)(w + o_pb), dinf);
+    k_proof_stage2<<<2, 32, 0, st>>>(mid, (const uint32_t *)(w + o_scal), prod);
+    k_proof_stage3<<<2, 32, 0, st>>>(mid, prod, r1, (g1_affine_t *)(w + o_pa), (g1_affine_t *)(w + o_pc), dinf);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    uint32_t status[8];
+    uint8_t inf3[4];
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_a, w + o_pa, 96, cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_b, w + o_pb, 192, cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_c, w + o_pc, 96, cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(inf3, dinf, 3, cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(status, stw, sizeof(status), cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int j = 0; j < 8; j++) {
+        if (status[j] == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status[j], "UnexpectedIdentity in multiexp");
+        if (status[j] == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status[j], "IoError(UnexpectedEof) in multiexp");
+    }
+    if (inf_flags) { inf_flags[0] = inf3[0]; inf_flags[1] = inf3[1]; inf_flags[2] = inf3[2]; }
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk

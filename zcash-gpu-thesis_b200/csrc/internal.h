@@ -49,6 +49,8 @@ struct Ctx {
     size_t scratch_bytes = 0;
     void *scratch2 = nullptr;
     size_t scratch2_bytes = 0;
+    void *scratch3 = nullptr;  // groth16 prover workspace
+    size_t scratch3_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // NCCL (loaded lazily, only when a communicator is requested)
     void *nccl_comm = nullptr;
@@ -88,5 +90,23 @@ int msm_fixed_base(Ctx *ctx, int group, const void *d_base_affine, const void *d
                    uint8_t *d_out_inf);
 int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf);
 int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out);
+int msm_build_table(Ctx *ctx, int group, const void *d_base_affine, void *d_table, uint32_t nwin);  // 255 * nwin XYZZ entries
+// groth16.cu
+struct Crs {
+    Ctx *ctx;
+    Bases *h, *l, *a, *b_g1, *b_g2;
+    void *vk;            // device: alpha_g1 | beta_g1 | delta_g1 (3 x 96 B) | beta_g2 | delta_g2 (2 x 192 B)
+    void *table_delta_g1;  // 32 x 255 XYZZ<fq>
+    void *table_delta_g2;  // 32 x 255 XYZZ<fq2>
+    bool subverted;      // delta_g1 or delta_g2 is the identity (prover.rs:320-324)
+};
+struct ProveArgs {
+    const uint64_t *a, *b, *c; size_t n_constraints;
+    const uint64_t *inputs; size_t n_inputs;
+    const uint64_t *aux; size_t n_aux;
+    const uint8_t *a_aux_density, *b_input_density, *b_aux_density;
+    const uint64_t *r, *s;
+};
+int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &args, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c, uint8_t *inf_flags);
 
 }  // namespace b200zk

@@ -7,7 +7,8 @@ namespace b200zk {
     int msm_run_##SUFFIX(Ctx *, const Bases *, size_t, const void *, size_t, const uint8_t *, void *, void *, int);                  \
     int msm_fixed_base_##SUFFIX(Ctx *, const void *, const void *, size_t, uint32_t, void *, uint8_t *);                             \
     int msm_into_affine_##SUFFIX(Ctx *, const void *, size_t, void *, uint8_t *);                                                    \
-    int msm_sum_points_##SUFFIX(Ctx *, const void *, size_t, void *);
+    int msm_sum_points_##SUFFIX(Ctx *, const void *, size_t, void *);                                                                \
+    int msm_build_table_##SUFFIX(Ctx *, const void *, void *, uint32_t);
 DECL(g1)
 DECL(g2)
 
@@ -31,6 +32,11 @@ int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_
     if (group == B200ZK_G1) return msm_sum_points_g1(ctx, d_jac_in, n, d_jac_out);
     if (group == B200ZK_G2) return msm_sum_points_g2(ctx, d_jac_in, n, d_jac_out);
     return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
+}
+
+int msm_build_table(Ctx *ctx, int group, const void *d_base_affine, void *d_table, uint32_t nwin) {
+    if (group == B200ZK_G1) return msm_build_table_g1(ctx, d_base_affine, d_table, nwin);
+    return msm_build_table_g2(ctx, d_base_affine, d_table, nwin);
 }
 
 }  // namespace b200zk

@@ -421,6 +421,11 @@ static int msm_sum_points_t(Ctx *ctx, const void *d_jac_in, size_t n, void *d_ja
     int msm_into_affine_##SUFFIX(Ctx *ctx, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf) {                       \
         return msm_into_affine_t<F>(ctx, d_jac, n, d_out_xy, d_out_inf);                                                           \
     }                                                                                                                              \
-    int msm_sum_points_##SUFFIX(Ctx *ctx, const void *d_jac_in, size_t n, void *d_jac_out) { return msm_sum_points_t<F>(ctx, d_jac_in, n, d_jac_out); }
+    int msm_sum_points_##SUFFIX(Ctx *ctx, const void *d_jac_in, size_t n, void *d_jac_out) { return msm_sum_points_t<F>(ctx, d_jac_in, n, d_jac_out); } \
+    int msm_build_table_##SUFFIX(Ctx *ctx, const void *d_base_affine, void *d_table, uint32_t nwin) {                                 \
+        k_fixed_base_table<F><<<1, 32, 0, ctx->stream>>>((const Affine<F> *)d_base_affine, (XYZZ<F> *)d_table, nwin);                 \
+        B200ZK_CUDA(ctx, cudaGetLastError());                                                                                         \
+        return B200ZK_OK;                                                                                                             \
+    }
 
 }  // namespace b200zk
