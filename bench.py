@@ -209,11 +209,7 @@ def main():
     # ---- synthetic inputs: bases [k_i]G generated on the device, uniform scalars from the host
     k = np.zeros((n, 4), dtype=np.uint64)
     k[:, 0] = rng.integers(1, 1 << 64, size=n, dtype=np.uint64)
-    gen_x = 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
-    gen_y = 0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1
-    q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
-    R = (1 << 384) % q
-    gen = np.array([((v * R % q) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for v in (gen_x, gen_y) for i in range(6)], dtype=np.uint64)
+    gen = gen_g1_limbs()
     dxy, dinf, _ = zk.fixed_base_mul(w, zk.G1, gen, k, 64)
     bases = zk.Bases.from_device(w, zk.G1, dxy, n)
     dxy.free(); dinf.free()
@@ -309,7 +305,11 @@ def main():
     e2e_value = world * n / (e2e_ms * 1e-3)
 
     # ---- roofline for the dominant kernel (bucket accumulation), integer pipe
-    int_peak = w.microbench(1, 4000)  # IMAD.WIDE/s measured live on this GPU (32x32+64 multiply-adds)
+    # The multiplier pipe (fmaheavy) issues one 32x32->64 IMAD.WIDE per 4 cycles per SM sub-partition = 32/clk/SM (ncu:
+    # 94.8 % pipe-busy at 9.24 T wide-IMAD/s, profiles/r01_mulbench_ncu_pipes.csv); plain 32-bit IMAD is 64/clk/SM.
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    int_peak = 32.0 * w.sm_count() * sm_mhz * 1e6
+    wide_measured = w.microbench(1, 4000)  # dependent mad.wide chains, measured live (a lower bound of the pipe rate)
     c_ref, w_ref = windows_reference(n)
     alg_imad = n * 3300.0 * w_ref  # W(n) mixed adds x 11 Fq-mul-equiv x 300 IMAD per point
     acc_launch_ms = acc_ms.value / max(acc_n.value, 1)
@@ -325,9 +325,11 @@ def main():
         "kernel": "k_msm_accumulate<fq_t>", "bound": "int32",
         "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "TIMAD/s", "frac": achieved / int_peak if int_peak else None,
         "traffic": None,
-        "note": "MSM is bound by the INT32 multiply-add pipe (no dense contraction, HBM-light): achieved = algorithmic IMADs of the reference "
-                "algorithm (3300*W(n) per point, W(2^24)=15 windows of c=17) / measured accumulate-kernel time; peak = IMAD.WIDE rate measured "
-                "live by b200zk_microbench. The kernel does fewer real IMADs than the reference formula (signed 16-bit windows, XYZZ adds).",
+        "note": "MSM is bound by the INT32 multiplier pipe (no dense contraction, HBM-light): achieved = algorithmic 32x32->64 multiply-adds of "
+                "the reference algorithm (3300*W(n) per point, W(2^24)=15 windows of c=17; SURVEY.md 8d) / measured accumulate-kernel time; peak = "
+                "32 IMAD.WIDE/clk/SM x SMs x sampled SM clock (the fmaheavy pipe rate established with ncu); the 64/clk/SM figure of plain 32-bit "
+                "IMAD does not apply to 64-bit products.",
+        "imad_wide_measured_TIMADps": wide_measured / 1e12,
         "kernel_ms_per_launch": acc_launch_ms, "kernel_share_of_step": acc_launch_ms / ms_step if ms_step else None,
         "hbm": {"algorithmic_GB": alg_bytes / 1e9, "achieved_GBps": alg_bytes / 1e9 / (acc_launch_ms * 1e-3) if acc_launch_ms else None,
                 "peak_GBps": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
@@ -400,7 +402,124 @@ def bench_extra(w, zk, lib, rng, timed, world):
     out["spend_h_poly_2^17"] = {"per_s": world * 1e3 / ms, "ms": ms}
     for x in (a, b, c, o):
         x.free()
+    out["sapling_spend_proofs"] = bench_spend_proofs(w, zk, rng, world)
     return out
+
+
+def bench_spend_proofs(w, zk, rng, world):
+    """Sapling-Spend-shaped create_proof: 98 785 constraints -> m = 2^17; H 131 071, L 98 638, A 8 + 85 382,
+    B 1 + 61 299 (G1 and G2) bases; witness-like scalars (half of them 0/1).  The CRS is synthetic ([k]G points generated on
+    the device), so the proofs are not meaningful -- the arithmetic is identical to a real Spend proof.  Proofs of a batch
+    are independent: each rank proves its own share on `streams` concurrent contexts."""
+    import threading
+
+    from zcash_gpu_thesis_b200 import _lib as L
+
+    n_con, n_in, n_aux = 98785, 8, 98638
+    a_dense, b_in_dense, b_aux_dense = 85382, 1, 61299
+    g1 = gen_g1_limbs()
+    g2 = gen_g2_limbs()
+
+    def bases(group, n, gen):
+        k = np.zeros((n, 4), dtype=np.uint64)
+        k[:, 0] = rng.integers(1, 1 << 64, size=n, dtype=np.uint64)
+        dxy, dinf, _ = zk.fixed_base_mul(w, group, gen, k, 64)
+        b = zk.Bases.from_device(w, group, dxy, n)
+        dxy.free(); dinf.free()
+        return b
+
+    h, l = bases(L.G1, (1 << 17) - 1, g1), bases(L.G1, n_aux, g1)
+    a, b1, b2 = bases(L.G1, n_in + a_dense, g1), bases(L.G1, b_in_dense + b_aux_dense, g1), bases(L.G2, b_in_dense + b_aux_dense, g2)
+    head1 = np.zeros((3, 12), dtype=np.uint64)
+    st = w.lib.b200zk_d2h(w.ctx, head1.ctypes.data_as(ctypes.c_void_p), bases_ptr(w, zk, L.G1, g1, rng, 3), 3 * 96)
+    head2 = np.zeros((2, 24), dtype=np.uint64)
+    st |= w.lib.b200zk_d2h(w.ctx, head2.ctypes.data_as(ctypes.c_void_p), bases_ptr(w, zk, L.G2, g2, rng, 2), 2 * 192)
+    assert st == 0
+    params = zk.Parameters(w, h, l, a, b1, b2, head1[0], head1[1], head2[0], head1[2], head2[1])
+
+    def witness(n):
+        v = random_scalars(rng, n)
+        small = rng.random(n) < 0.5
+        v[small] = 0
+        v[small, 0] = rng.integers(0, 2, size=int(small.sum()), dtype=np.uint64)
+        return v
+
+    def density(n, total):
+        d = np.zeros(n, dtype=np.uint8)
+        d[rng.choice(n, size=total, replace=False)] = 1
+        return d
+
+    ev = [random_scalars(rng, n_con) for _ in range(3)]
+    inputs, aux = witness(n_in), witness(n_aux)
+    inputs[0] = (1, 0, 0, 0)
+    da, dbi, dba = density(n_aux, a_dense), density(n_in, b_in_dense), density(n_aux, b_aux_dense)
+    r, s = 0x1234567890ABCDEF1234567890ABCDEF, 0x0FEDCBA0987654321FEDCBA098765432
+
+    def prove(worker):
+        return zk.create_proof_from_assignment(worker, params, ev[0], ev[1], ev[2], inputs, aux, da, dbi, dba, r, s)
+
+    p0 = prove(w)
+    p1 = prove(w)
+    assert np.array_equal(p0.a, p1.a) and np.array_equal(p0.c, p1.c)  # deterministic
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        prove(w)
+    single_ms = (time.perf_counter() - t0) / reps * 1e3
+    streams = 4
+    workers = [zk.Worker(w.device) for _ in range(streams)]
+    for x in workers:
+        prove(x)
+    per_thread = 6
+
+    def loop(x):
+        for _ in range(per_thread):
+            prove(x)
+
+    ths = [threading.Thread(target=loop, args=(x,)) for x in workers]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    for x in workers:
+        x.close()
+    return {"proofs_per_s": world * streams * per_thread / dt, "single_stream_ms_per_proof": single_ms, "streams_per_gpu": streams,
+            "batch": world * streams * per_thread, "timing": "host wall clock around b200zk_groth16_prove incl. H2D of a/b/c/assignments and D2H of the proof",
+            "shape": "m=2^17, MSM sizes 131071/98638/8+85382/1+61299 (G1) and 1+61299 (G2), synthetic CRS"}
+
+
+def gen_g1_limbs():
+    gx = 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
+    gy = 0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1
+    return fq_mont_limbs([gx, gy])
+
+
+def gen_g2_limbs():
+    x0 = 0x024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8
+    x1 = 0x13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e
+    y0 = 0x0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801
+    y1 = 0x0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be
+    return fq_mont_limbs([x0, x1, y0, y1])
+
+
+def fq_mont_limbs(vals):
+    q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    R = (1 << 384) % q
+    return np.array([((v * R % q) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for v in vals for i in range(6)], dtype=np.uint64)
+
+
+_KEEP = []
+
+
+def bases_ptr(w, zk, group, gen, rng, n):
+    """n device-generated points [k]G as a raw device pointer (kept alive for the duration of the bench)"""
+    k = np.zeros((n, 4), dtype=np.uint64)
+    k[:, 0] = rng.integers(1, 1 << 64, size=n, dtype=np.uint64)
+    dxy, dinf, _ = zk.fixed_base_mul(w, group, gen, k, 64)
+    _KEEP.append((dxy, dinf))
+    return dxy.ptr
 
 
 def bench_cpu_baseline(bases_k, scalars, gen):

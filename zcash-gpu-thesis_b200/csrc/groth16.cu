@@ -1,5 +1,5 @@
 // The numeric pipeline of groth16::create_proof (bellman/src/groth16/prover.rs:249-364) on the device:
-// H polynomial (7 NTTs + pointwise, prover.rs:256-287) -> 8 multiexps (prover.rs:289-318) -> proof assembly
+// H polynomial (7 NTTs + pointwise, prover.rs:256-287) -> the multiexps of prover.rs:289-318 -> proof assembly
 // (prover.rs:326-363).  Circuit synthesis (prover.rs:212-234) stays on the host: the caller passes the a/b/c
 // evaluation vectors, the input / aux assignments and the three density maps that ProvingAssignment collects.
 //
@@ -15,8 +15,11 @@
 
 namespace b200zk {
 
-enum { R_H = 0, R_L, R_A_IN, R_A_AUX, R_B1_IN, R_B1_AUX, R_COUNT_G1 };  // G1 multiexp results (Jacobian, 144 B each)
-enum { R_B2_IN = 0, R_B2_AUX, R_COUNT_G2 };                             // G2 results (288 B each)
+// The reference issues a_inputs / a_aux (and the B pairs) as separate multiexps over the *same* base vector with the aux
+// cursor starting right after the inputs (groth16/mod.rs:456-481); only their sums are used (prover.rs:339-347), so each
+// pair is one multiexp over inputs ++ aux with the concatenated density map.
+enum { R_H = 0, R_L, R_A, R_B1, R_COUNT_G1 };  // G1 multiexp results (Jacobian, 144 B each)
+enum { R_B2 = 0, R_COUNT_G2 };                  // G2 result (288 B)
 
 // scal[0] = r, scal[1] = s  (canonical FrRepr, 8 u32 each)
 // block 0: T = r * delta_g1 (table), g_a = T + alpha_g1 + a_in + a_aux ; B1 = beta_g1 + b1_in + b1_aux
@@ -49,12 +52,10 @@ __global__ void __launch_bounds__(32) k_proof_stage1(const g1_xyzz_t *table_d1, 
         table_mul_warp<fq_t>(table_d1, scal, sm, t);
         if (threadIdx.x == 0) {
             t.add_mixed(vk_g1[0], false);
-            t.add(g1_xyzz_t::from_jacobian(res_g1[R_A_IN]));
-            t.add(g1_xyzz_t::from_jacobian(res_g1[R_A_AUX]));
+            t.add(g1_xyzz_t::from_jacobian(res_g1[R_A]));
             out_g1[0] = t.to_jacobian();
             g1_xyzz_t b1 = g1_xyzz_t::from_affine(vk_g1[1]);
-            b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1_IN]));
-            b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1_AUX]));
+            b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1]));
             out_g1[1] = b1.to_jacobian();
         }
     } else {
@@ -63,8 +64,7 @@ __global__ void __launch_bounds__(32) k_proof_stage1(const g1_xyzz_t *table_d1, 
         table_mul_warp<fq2_t>(table_d2, scal + 8, sm, t);
         if (threadIdx.x == 0) {
             t.add_mixed(vk_g2[0], false);
-            t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2_IN]));
-            t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2_AUX]));
+            t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2]));
             g2_affine_t a;
             bool ok = jacobian_to_affine(t.to_jacobian(), a);
             *proof_b = a;
@@ -128,8 +128,9 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
     size_t o_a = take(vec), o_b = take(vec), o_c = take(vec), o_h = take(vec);
-    size_t o_in = take(g.n_inputs * 32), o_aux = take(g.n_aux * 32);
-    size_t o_da = take(g.n_aux), o_dbi = take(g.n_inputs), o_dba = take(g.n_aux);
+    const size_t n_all = g.n_inputs + g.n_aux;
+    size_t o_in = take(n_all * 32), o_aux = o_in + g.n_inputs * 32;  // inputs ++ aux, contiguous
+    size_t o_da = take(n_all), o_db = take(n_all);                   // [1..1] ++ a_aux_density ; b_input_density ++ b_aux_density
     size_t o_scal = take(64), o_r1 = take(R_COUNT_G1 * 144), o_r2 = take(R_COUNT_G2 * 288), o_st = take(8 * 4);
     size_t o_mid = take(2 * 144), o_prod = take(2 * 144), o_pa = take(96), o_pb = take(192), o_pc = take(96), o_inf = take(4);
     int rc = ensure_scratch(ctx, &ctx->scratch3, &ctx->scratch3_bytes, off);
@@ -148,14 +149,12 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     }
     B200ZK_CUDA(ctx, up(o_in, g.inputs, g.n_inputs * 32));
     B200ZK_CUDA(ctx, up(o_aux, g.aux, g.n_aux * 32));
-    B200ZK_CUDA(ctx, up(o_da, g.a_aux_density, g.n_aux));
-    B200ZK_CUDA(ctx, up(o_dbi, g.b_input_density, g.n_inputs));
-    B200ZK_CUDA(ctx, up(o_dba, g.b_aux_density, g.n_aux));
+    if (g.n_inputs) B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_da, 1, g.n_inputs, st));  // inputs have full density in A (prover.rs:148-151)
+    B200ZK_CUDA(ctx, up(o_da + g.n_inputs, g.a_aux_density, g.n_aux));
+    B200ZK_CUDA(ctx, up(o_db, g.b_input_density, g.n_inputs));
+    B200ZK_CUDA(ctx, up(o_db + g.n_inputs, g.b_aux_density, g.n_aux));
     B200ZK_CUDA(ctx, up(o_scal, g.r, 32));
     B200ZK_CUDA(ctx, up(o_scal + 32, g.s, 32));
-    // b_input_density_total decides where the aux cursor of the B queries starts (prover.rs:305-315)
-    size_t b_in_total = 0;
-    for (size_t i = 0; i < g.n_inputs; i++) b_in_total += g.b_input_density[i] ? 1 : 0;
 
     // ---- H polynomial (prover.rs:256-287)
     if ((rc = ntt_h_poly(ctx, w + o_a, w + o_b, w + o_c, log_m, w + o_h))) return rc;
@@ -163,19 +162,17 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     g1_jac_t *r1 = (g1_jac_t *)(w + o_r1);
     g2_jac_t *r2 = (g2_jac_t *)(w + o_r2);
     uint32_t *stw = (uint32_t *)(w + o_st);
-    const uint8_t *da = (const uint8_t *)(w + o_da), *dbi = (const uint8_t *)(w + o_dbi), *dba = (const uint8_t *)(w + o_dba);
+    const uint8_t *da = (const uint8_t *)(w + o_da), *db = (const uint8_t *)(w + o_db);
     struct Job { const Bases *b; size_t off; size_t src; size_t n; const uint8_t *d; void *out; };
-    Job jobs[8] = {
+    const int n_jobs = 5;
+    Job jobs[n_jobs] = {
         {crs->h, 0, o_h, m - 1, nullptr, &r1[R_H]},
         {crs->l, 0, o_aux, g.n_aux, nullptr, &r1[R_L]},
-        {crs->a, 0, o_in, g.n_inputs, nullptr, &r1[R_A_IN]},
-        {crs->a, g.n_inputs, o_aux, g.n_aux, da, &r1[R_A_AUX]},
-        {crs->b_g1, 0, o_in, g.n_inputs, dbi, &r1[R_B1_IN]},
-        {crs->b_g1, b_in_total, o_aux, g.n_aux, dba, &r1[R_B1_AUX]},
-        {crs->b_g2, 0, o_in, g.n_inputs, dbi, &r2[R_B2_IN]},
-        {crs->b_g2, b_in_total, o_aux, g.n_aux, dba, &r2[R_B2_AUX]},
+        {crs->a, 0, o_in, n_all, da, &r1[R_A]},
+        {crs->b_g1, 0, o_in, n_all, db, &r1[R_B1]},
+        {crs->b_g2, 0, o_in, n_all, db, &r2[R_B2]},
     };
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < n_jobs; j++) {
         if ((rc = msm_run(ctx, jobs[j].b, jobs[j].off, w + jobs[j].src, jobs[j].n, jobs[j].d, jobs[j].out, stw + j, 0))) return rc;
     }
     // ---- assembly (prover.rs:326-363)
@@ -196,7 +193,7 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     B200ZK_CUDA(ctx, cudaMemcpyAsync(inf3, dinf, 3, cudaMemcpyDeviceToHost, st));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(status, stw, sizeof(status), cudaMemcpyDeviceToHost, st));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < n_jobs; j++) {
         if (status[j] == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status[j], "UnexpectedIdentity in multiexp");
         if (status[j] == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status[j], "IoError(UnexpectedEof) in multiexp");
     }

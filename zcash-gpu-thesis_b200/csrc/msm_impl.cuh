@@ -166,19 +166,79 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
 #ifndef B200ZK_ACC_MINBLOCKS
 #define B200ZK_ACC_MINBLOCKS 3
 #endif
+// Oversized buckets (witness scalars are full of 0/1/small values: half of a Sapling witness lands in bucket 1 of
+// window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
+// split bucket are folded by one warp (k_msm_combine_split).  Uniform scalars never split (cap = 2 x mean + slack).
+static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, uint32_t n_buckets, uint32_t cap, uint32_t *__restrict__ task_cnt,
+                                         uint32_t *__restrict__ split_list, uint32_t *__restrict__ n_split) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    uint32_t cnt = offsets[b + 1] - offsets[b];
+    uint32_t tasks = cnt <= cap ? 0u : (cnt + cap - 1) / cap;
+    task_cnt[b] = tasks;
+    if (tasks) split_list[atomicAdd(n_split, 1u)] = b;
+}
+
 template <class F>
 __global__ void __launch_bounds__(128, B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                                                       const uint32_t *__restrict__ offsets, uint32_t n_buckets, XYZZ<F> *__restrict__ buckets) {
+                                                       const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
+                                                       const uint32_t *__restrict__ task_off, uint32_t cap, XYZZ<F> *__restrict__ buckets,
+                                                       XYZZ<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_buckets) return;
-    uint32_t beg = offsets[t], end = offsets[t + 1];
+    uint32_t beg, end;
+    XYZZ<F> *dst;
+    if (t < n_buckets) {
+        if (task_cnt[t]) return;  // handled by its split tasks
+        beg = offsets[t];
+        end = offsets[t + 1];
+        dst = buckets + t;
+    } else {
+        uint32_t task = t - n_buckets;
+        if (task >= task_off[n_buckets]) return;
+        // bucket b with task_off[b] <= task < task_off[b + 1]
+        uint32_t lo = 0, hi = n_buckets;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (task_off[mid] <= task) lo = mid; else hi = mid;
+        }
+        uint32_t j = task - task_off[lo];
+        beg = offsets[lo] + j * cap;
+        end = min(beg + cap, offsets[lo + 1]);
+        dst = partials + task;
+    }
     XYZZ<F> acc = XYZZ<F>::zero();
     for (uint32_t k = beg; k < end; k++) {
         uint32_t e = sorted[k];
         Affine<F> p = bases[e & 0x7fffffffu];
         acc.add_mixed(p, (e >> 31) != 0);
     }
-    buckets[t] = acc;
+    *dst = acc;
+}
+
+// one warp per split bucket: lanes stride over the bucket's partial sums, then a shared-memory tree
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_combine_split(const uint32_t *__restrict__ split_list, const uint32_t *__restrict__ n_split,
+                                                         const uint32_t *__restrict__ task_cnt, const uint32_t *__restrict__ task_off,
+                                                         const XYZZ<F> *__restrict__ partials, XYZZ<F> *__restrict__ buckets) {
+    __shared__ XYZZ<F> sm[32];
+    const uint32_t total = *n_split;
+    for (uint32_t s = blockIdx.x; s < total; s += gridDim.x) {
+        uint32_t b = split_list[s], cnt = task_cnt[b], off = task_off[b];
+        XYZZ<F> acc = XYZZ<F>::zero();
+        for (uint32_t j = threadIdx.x; j < cnt; j += 32) acc.add(partials[off + j]);
+        sm[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t stride = 16; stride > 0; stride >>= 1) {
+            if (threadIdx.x < stride) {
+                XYZZ<F> t = sm[threadIdx.x];
+                t.add(sm[threadIdx.x + stride]);
+                sm[threadIdx.x] = t;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) buckets[b] = sm[0];
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ bucket reduction
@@ -275,6 +335,11 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_rank = take(d_density ? (n_exp + 1) * sizeof(uint32_t) : 0);
     size_t o_sorted = take(n_exp * sh.W * sizeof(uint32_t));
     size_t o_buckets = take(nbk * sizeof(XYZZ<F>));
+    // bucket splitting: cap = 2 x mean bucket load + 32; at most n*W/cap + nbk... split tasks, bounded by 2*n*W/cap
+    const uint32_t cap = (uint32_t)(2 * (n_exp / sh.B) + 32);
+    const size_t max_tasks = (size_t)2 * n_exp * sh.W / cap + 2;
+    size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
+    size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
     size_t lvl_entries = (size_t)sh.W * ((sh.B + RED_K - 1) / RED_K);
     size_t o_r0 = take(lvl_entries * sizeof(XYZZ<F>)), o_a0 = take(lvl_entries * sizeof(XYZZ<F>));
     size_t o_r1 = take(lvl_entries * sizeof(XYZZ<F>)), o_a1 = take(lvl_entries * sizeof(XYZZ<F>));
@@ -285,6 +350,8 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     uint32_t *cursor = (uint32_t *)(ws + o_cursor), *sums = (uint32_t *)(ws + o_sums), *rank = d_density ? (uint32_t *)(ws + o_rank) : nullptr;
     uint32_t *sorted = (uint32_t *)(ws + o_sorted);
     XYZZ<F> *buckets = (XYZZ<F> *)(ws + o_buckets);
+    uint32_t *task_cnt = (uint32_t *)(ws + o_tcnt), *task_off = (uint32_t *)(ws + o_toff), *split_list = (uint32_t *)(ws + o_split);
+    XYZZ<F> *partials = (XYZZ<F> *)(ws + o_partials);
     XYZZ<F> *lr[2] = {(XYZZ<F> *)(ws + o_r0), (XYZZ<F> *)(ws + o_r1)}, *la[2] = {(XYZZ<F> *)(ws + o_a0), (XYZZ<F> *)(ws + o_a1)};
 
     B200ZK_CUDA(ctx, cudaMemsetAsync(status, 0xff, 2 * sizeof(uint32_t), st));
@@ -303,7 +370,13 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
                                         sorted, status);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->prof_on) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
-    k_msm_accumulate<F><<<(unsigned)((nbk + 127) / 128), 128, 0, st>>>((const Affine<F> *)bases->points, sorted, offsets, (uint32_t)nbk, buckets);
+    uint32_t *n_split = status + 3;
+    B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, sizeof(uint32_t), st));
+    k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split);
+    scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
+    k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)bases->points, sorted, offsets, (uint32_t)nbk,
+                                                                                  task_cnt, task_off, cap, buckets, partials);
+    k_msm_combine_split<F><<<256, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
     // reduction tree
     const XYZZ<F> *inR = buckets, *inA = nullptr;
