@@ -92,6 +92,11 @@ int b200zk_bases_upload(b200zk_ctx *ctx, int group, const void *points, size_t n
                         size_t inf_stride, b200zk_bases **out);
 /* Same from device memory (packed x||y, optional infinity bytes). The data is copied. */
 int b200zk_bases_from_device(b200zk_ctx *ctx, int group, const void *d_points, size_t n, const uint8_t *d_infinity, b200zk_bases **out);
+/* Optional, one-time (CRS load): build the W-fold table 2^(c w) * P_i (affine) in HBM so that every Pippenger window adds
+ * into one shared bucket set -- the per-window joins of multiexp.rs:223-229 (c doublings each) and W - 1 of the W bucket
+ * reductions disappear and wider windows pay off.  Costs W x the base memory (12 x 1.5 GiB for 2^24 G1 points at c = 22).
+ * window_bits = 0 picks c from n.  Later multiexps on these bases use the table automatically.  Results are unchanged. */
+int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bits);
 size_t b200zk_bases_len(const b200zk_bases *bases);
 void b200zk_bases_free(b200zk_bases *bases);
 

@@ -227,3 +227,48 @@ def test_fixed_base_and_large_identity(worker):
     total = sum(int(x) * y for x, y in zip(kk, ee)) % Fr.p
     want_xy, want_inf = util.affine_of_scalar("g1", total)
     assert bool(inf[0]) == want_inf and np.array_equal(aff[0], want_xy)
+
+
+@pytest.mark.parametrize("group,n,c", [("g1", 1, 8), ("g1", 33, 9), ("g1", 3000, 0), ("g1", 3000, 13), ("g1", 1 << 14, 0), ("g2", 700, 0), ("g2", 700, 11)])
+def test_precomputed_bases_give_the_same_result(worker, group, n, c):
+    """b200zk_bases_precompute: the 2^(c w) * P table changes the schedule (one shared bucket set), not the result."""
+    import zcash_gpu_thesis_b200 as zk
+
+    code = zk.G1 if group == "g1" else zk.G2
+    r = util.rng(1300 + n + c)
+    xy, ks = util.random_bases(group, r, n + 50)
+    exps = util.random_fr_repr(r, n)
+    exps[0] = int_to_limbs(Fr.p - 1, 4)
+    if n > 10:
+        exps[3] = 0
+        exps[4] = (1, 0, 0, 0)
+    bases = zk.Bases(worker, code, xy).precompute(c)
+    _check(worker, group, xy, exps, bases=bases)
+    density = (r.random(n) < 0.6).astype(np.uint8)
+    aff, inf = _check(worker, group, xy, exps, density=density, offset=17, bases=bases)
+    want_xy, want_inf = util.affine_of_scalar(group, util.expected_scalar(ks, exps, density, 17))
+    assert inf == want_inf and (inf or np.array_equal(aff, want_xy))
+    # witness-like scalars: a large share of 0 / 1 / small values (splits the oversized buckets)
+    small = exps.copy()
+    mask = r.random(n) < 0.7
+    small[mask] = 0
+    small[mask, 0] = r.integers(0, 3, size=int(mask.sum()), dtype=np.uint64)
+    _check(worker, group, xy, small, bases=bases)
+    # too few bases still reports UnexpectedEof
+    with pytest.raises(zk.IoError):
+        zk.multiexp(worker, (bases, 60), zk.FullDensity(), np.concatenate([exps, exps])[: n + 10])
+
+
+def test_witness_like_scalars_split_buckets(worker):
+    """Half of the exponents equal to one (a Sapling witness is full of boolean wires): the oversized bucket is split into
+    tasks and folded by a warp; the result must not change."""
+    n = 20000
+    r = util.rng(1400)
+    xy, ks = util.random_bases("g1", r, n)
+    exps = util.random_fr_repr(r, n)
+    ones = r.random(n) < 0.5
+    exps[ones] = (1, 0, 0, 0)
+    exps[r.random(n) < 0.2] = 0
+    aff, inf = _check(worker, "g1", xy, exps)
+    want_xy, want_inf = util.affine_of_scalar("g1", util.expected_scalar(ks, exps))
+    assert inf == want_inf and np.array_equal(aff, want_xy)

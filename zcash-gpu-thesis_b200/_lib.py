@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200zk_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "b200zk_bases_upload": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, C.POINTER(_vp)]),
     "b200zk_bases_from_device": (_i, [_vp, _i, _vp, _sz, _vp, C.POINTER(_vp)]),
+    "b200zk_bases_precompute": (_i, [_vp, _vp, _i]),
     "b200zk_bases_len": (_sz, [_vp]),
     "b200zk_bases_free": (None, [_vp]),
     "b200zk_multiexp": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),

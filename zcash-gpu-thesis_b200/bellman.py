@@ -251,6 +251,13 @@ class Bases:
     def __len__(self):
         return self.n
 
+    def precompute(self, window_bits=0):
+        """Build the 2^(c w) * P table in HBM (one-time, at CRS load); multiexps on these bases then share one bucket set."""
+        st = self.worker.lib.b200zk_bases_precompute(self.worker.ctx, self.handle, window_bits)
+        if st:
+            _raise(self.worker, st)
+        return self
+
     def free(self):
         if getattr(self, "handle", None) is not None and self.worker.ctx is not None:
             self.worker.lib.b200zk_bases_free(self.handle)

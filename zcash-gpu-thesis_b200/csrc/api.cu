@@ -235,6 +235,21 @@ int b200zk_bases_upload(b200zk_ctx *ctx, int group, const void *points, size_t n
     return B200ZK_OK;
 }
 
+int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bits) {
+    CHECK_CTX(ctx);
+    if (!bases) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null bases");
+    USE_DEVICE(ctx);
+    uint32_t c = (uint32_t)window_bits;
+    if (window_bits <= 0) {  // automatic: about log2(n) - 2, so that the single bucket set costs a few percent of the adds
+        uint32_t lg = 0;
+        while (((size_t)1 << (lg + 1)) <= bases->n) lg++;
+        c = lg > 2 ? lg - 2 : 8;
+        if (c < 8) c = 8;
+        if (c > 22) c = 22;
+    }
+    return msm_precompute(ctx, bases, c);
+}
+
 size_t b200zk_bases_len(const b200zk_bases *bases) { return bases ? bases->n : 0; }
 
 void b200zk_bases_free(b200zk_bases *bases) {
@@ -243,6 +258,7 @@ void b200zk_bases_free(b200zk_bases *bases) {
     cudaStreamSynchronize(bases->ctx->stream);
     cudaFree(bases->points);
     cudaFree(bases->infinity);
+    cudaFree(bases->pre);
     delete bases;
 }
 

@@ -69,6 +69,8 @@ struct Bases {
     size_t n;
     void *points;       // device, x||y Montgomery
     uint8_t *infinity;  // device, n bytes, or nullptr when no base is the identity
+    void *pre = nullptr;  // optional: pre[w * n + i] = 2^(c w) * points[i], w < pre_W (b200zk_bases_precompute)
+    uint32_t pre_c = 0, pre_W = 0;
 };
 
 // ---- launchers implemented in the .cu files (all enqueue on ctx->stream, no implicit sync)
@@ -90,6 +92,7 @@ int msm_fixed_base(Ctx *ctx, int group, const void *d_base_affine, const void *d
                    uint8_t *d_out_inf);
 int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf);
 int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out);
+int msm_precompute(Ctx *ctx, Bases *bases, uint32_t c);
 int msm_build_table(Ctx *ctx, int group, const void *d_base_affine, void *d_table, uint32_t nwin);  // 255 * nwin XYZZ entries
 // groth16.cu
 struct Crs {

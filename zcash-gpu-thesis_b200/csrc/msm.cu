@@ -8,7 +8,8 @@ namespace b200zk {
     int msm_fixed_base_##SUFFIX(Ctx *, const void *, const void *, size_t, uint32_t, void *, uint8_t *);                             \
     int msm_into_affine_##SUFFIX(Ctx *, const void *, size_t, void *, uint8_t *);                                                    \
     int msm_sum_points_##SUFFIX(Ctx *, const void *, size_t, void *);                                                                \
-    int msm_build_table_##SUFFIX(Ctx *, const void *, void *, uint32_t);
+    int msm_build_table_##SUFFIX(Ctx *, const void *, void *, uint32_t);                                                             \
+    int msm_precompute_##SUFFIX(Ctx *, Bases *, uint32_t);
 DECL(g1)
 DECL(g2)
 
@@ -34,6 +35,9 @@ int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_
     return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
 }
 
+int msm_precompute(Ctx *ctx, Bases *bases, uint32_t c) {
+    return bases->group == B200ZK_G1 ? msm_precompute_g1(ctx, bases, c) : msm_precompute_g2(ctx, bases, c);
+}
 int msm_build_table(Ctx *ctx, int group, const void *d_base_affine, void *d_table, uint32_t nwin) {
     if (group == B200ZK_G1) return msm_build_table_g1(ctx, d_base_affine, d_table, nwin);
     return msm_build_table_g2(ctx, d_base_affine, d_table, nwin);

@@ -112,6 +112,7 @@ static void scan_u32(cudaStream_t st, const T *in, size_t n, uint32_t *out, uint
 // ------------------------------------------------------------------------------------------------ digits / sort
 struct MsmShape {
     uint32_t c, W, B;  // window bits, windows (c*W >= 256), buckets per window = 2^(c-1)
+    uint32_t pre_n;    // 0, or the stride of the precomputed base table (then all windows share one bucket set)
 };
 
 __device__ __forceinline__ uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
@@ -152,12 +153,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
         uint32_t d = neg ? (1u << sh.c) - raw : raw;
         carry = neg;
         if (d == 0) continue;
-        uint32_t slot = w * sh.B + d - 1;
+        // with precomputed 2^(c w) * P the digit of window w is a digit of window 0 for the point w * n + idx
+        uint32_t slot = (sh.pre_n ? 0u : w * sh.B) + d - 1;
         if (MODE == 0) {
             atomicAdd(&counts_or_cursor[slot], 1u);
         } else {
             uint32_t pos = atomicAdd(&counts_or_cursor[slot], 1u);
-            sorted[pos] = (uint32_t)idx | (neg << 31);
+            sorted[pos] = (uint32_t)(idx + (size_t)w * sh.pre_n) | (neg << 31);
         }
     }
 }
@@ -328,12 +330,16 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     cudaStream_t st = ctx->stream;
     if (n_exp >= (1ull << 31) || bases->n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "n >= 2^31 not supported");
     MsmShape sh;
-    sh.c = window_bits > 0 ? (uint32_t)window_bits : msm_default_window(n_exp);
+    const bool use_pre = bases->pre != nullptr && (window_bits <= 0 || (uint32_t)window_bits == bases->pre_c);
+    sh.c = use_pre ? bases->pre_c : window_bits > 0 ? (uint32_t)window_bits : msm_default_window(n_exp);
     if (sh.c < 2 || sh.c > 24) return set_error(ctx, B200ZK_ERR_BAD_ARG, "window bits must be in [2, 24]");
     sh.W = (256 + sh.c - 1) / sh.c;
     sh.B = 1u << (sh.c - 1);
-    const size_t nbk = (size_t)sh.W * sh.B;
+    sh.pre_n = use_pre ? (uint32_t)bases->n : 0u;
+    const uint32_t bw = use_pre ? 1u : sh.W;  // bucket sets
+    const size_t nbk = (size_t)bw * sh.B;
     if (nbk + n_exp * sh.W >= (1ull << 32)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "n * windows >= 2^32 not supported");
+    const void *point_table = use_pre ? bases->pre : bases->points;
 
     // workspace carve-up
     size_t off = 0;
@@ -347,12 +353,12 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_sorted = take(n_exp * sh.W * sizeof(uint32_t));
     size_t o_buckets = take(nbk * sizeof(XYZZ<F>));
     // bucket splitting: cap = 2 x mean bucket load + 32; at most n*W/cap + nbk... split tasks, bounded by 2*n*W/cap
-    const uint32_t cap = (uint32_t)(2 * (n_exp / sh.B) + 32);
+    const uint32_t cap = (uint32_t)(2 * (n_exp * (sh.W / bw) / sh.B) + 32);
     const size_t max_tasks = (size_t)2 * n_exp * sh.W / cap + 2;
     size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
     size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
     size_t o_shist = take((cap + 2) * sizeof(uint32_t)), o_scur = take((cap + 2) * sizeof(uint32_t)), o_order = take((nbk + 1) * sizeof(uint32_t));
-    size_t lvl_entries = (size_t)sh.W * ((sh.B + RED_K - 1) / RED_K);
+    size_t lvl_entries = (size_t)bw * ((sh.B + RED_K - 1) / RED_K);
     size_t o_r0 = take(lvl_entries * sizeof(XYZZ<F>)), o_a0 = take(lvl_entries * sizeof(XYZZ<F>));
     size_t o_r1 = take(lvl_entries * sizeof(XYZZ<F>)), o_a1 = take(lvl_entries * sizeof(XYZZ<F>));
     int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, off);
@@ -390,7 +396,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
     scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
     k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
-    k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)bases->points, sorted, offsets, (uint32_t)nbk,
+    k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
                                                                                   task_cnt, task_off, order, cap, buckets, partials);
     k_msm_combine_split<F><<<256, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
@@ -400,15 +406,66 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     int pp = 0;
     do {
         uint32_t n_out = (n_in + RED_K - 1) / RED_K;
-        uint32_t threads = n_out * sh.W;
-        k_msm_reduce_level<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, n_in, lr[pp], la[pp], n_out, sh.W, log_len);
+        uint32_t threads = n_out * bw;
+        k_msm_reduce_level<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, n_in, lr[pp], la[pp], n_out, bw, log_len);
         inR = lr[pp]; inA = la[pp];
         pp ^= 1;
         n_in = n_out;
         log_len += 5;
     } while (n_in > 1);
-    k_msm_window_combine<F><<<1, 1, 0, st>>>(inR, inA, sh, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
+    MsmShape comb = sh;
+    comb.W = bw;
+    k_msm_window_combine<F><<<1, 1, 0, st>>>(inR, inA, comb, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
     B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ base precomputation
+// pre[w * n + i] = 2^(c w) * P_i as affine points (w < W).  180 GB of HBM buys the W-fold table: every window then adds
+// into ONE bucket set -- no per-window bucket reduction, no c doublings per window join (multiexp.rs:223-229 disappears),
+// and c can grow until the single bucket set costs as much as a window (fewer mixed adds per point).
+template <class F>
+__global__ void __launch_bounds__(64) k_bases_precompute(const Affine<F> *__restrict__ points, size_t n, uint32_t c, uint32_t W, Affine<F> *__restrict__ pre) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = points[i];
+    pre[i] = p;
+    Jacobian<F> j = {p.x, p.y, F::one()};
+    F zs[31], pz[31];
+    F run = F::one();
+    for (uint32_t w = 1; w < W; w++) {
+        for (uint32_t k = 0; k < c; k++) jacobian_double(j);
+        Affine<F> t = {j.x, j.y};
+        pre[(size_t)w * n + i] = t;
+        zs[w - 1] = j.z;
+        run = run * j.z;
+        pz[w - 1] = run;
+    }
+    F inv = run.inverse();  // one inversion per base (Montgomery's trick over its W - 1 multiples)
+    for (uint32_t w = W - 1; w >= 1; w--) {
+        F zinv = w > 1 ? inv * pz[w - 2] : inv;
+        inv = inv * zs[w - 1];
+        Affine<F> t = pre[(size_t)w * n + i];
+        F zi2 = zinv.sqr();
+        t.x = t.x * zi2;
+        t.y = t.y * (zi2 * zinv);
+        pre[(size_t)w * n + i] = t;
+    }
+}
+template <class F>
+static int msm_precompute_t(Ctx *ctx, Bases *bases, uint32_t c) {
+    if (c < 2 || c > 24) return set_error(ctx, B200ZK_ERR_BAD_ARG, "window bits must be in [2, 24]");
+    uint32_t W = (256 + c - 1) / c;
+    if (W > 32) return set_error(ctx, B200ZK_ERR_BAD_ARG, "window too narrow for precomputation (more than 32 windows)");
+    if ((size_t)W * bases->n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "precomputed table would exceed 2^31 points");
+    if (bases->pre) { cudaFree(bases->pre); bases->pre = nullptr; bases->pre_c = bases->pre_W = 0; }
+    if (bases->n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaMalloc(&bases->pre, (size_t)W * bases->n * sizeof(Affine<F>)));
+    k_bases_precompute<F><<<(unsigned)((bases->n + 63) / 64), 64, 0, ctx->stream>>>((const Affine<F> *)bases->points, bases->n, c, W, (Affine<F> *)bases->pre);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bases->pre_c = c;
+    bases->pre_W = W;
     return B200ZK_OK;
 }
 
@@ -511,6 +568,7 @@ static int msm_sum_points_t(Ctx *ctx, const void *d_jac_in, size_t n, void *d_ja
         return msm_into_affine_t<F>(ctx, d_jac, n, d_out_xy, d_out_inf);                                                           \
     }                                                                                                                              \
     int msm_sum_points_##SUFFIX(Ctx *ctx, const void *d_jac_in, size_t n, void *d_jac_out) { return msm_sum_points_t<F>(ctx, d_jac_in, n, d_jac_out); } \
+    int msm_precompute_##SUFFIX(Ctx *ctx, Bases *bases, uint32_t c) { return msm_precompute_t<F>(ctx, bases, c); }                    \
     int msm_build_table_##SUFFIX(Ctx *ctx, const void *d_base_affine, void *d_table, uint32_t nwin) {                                 \
         k_fixed_base_table<F><<<1, 32, 0, ctx->stream>>>((const Affine<F> *)d_base_affine, (XYZZ<F> *)d_table, nwin);                 \
         B200ZK_CUDA(ctx, cudaGetLastError());                                                                                         \
