@@ -243,7 +243,9 @@ int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bit
     if (window_bits <= 0) {  // automatic: about log2(n) - 2, so that the single bucket set costs a few percent of the adds
         uint32_t lg = 0;
         while (((size_t)1 << (lg + 1)) <= bases->n) lg++;
-        c = lg > 2 ? lg - 2 : 8;
+        // small n: c = log2 n keeps ~50 points per bucket and tens of thousands of buckets (threads) in flight;
+        // large n: the single bucket set must stay a few percent of the adds
+        c = lg < 19 ? lg : lg - 1;
         if (c < 8) c = 8;
         if (c > 22) c = 22;
     }

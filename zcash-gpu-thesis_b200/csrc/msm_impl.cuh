@@ -12,7 +12,7 @@
 //   2. scan                  exclusive prefix sum of the histogram = bucket offsets
 //   3. k_msm_digits<SCATTER> counting-sort of (base index, sign) by bucket
 //   4. k_msm_accumulate      one thread per bucket, XYZZ accumulator in registers, mixed adds (the hot loop)
-//   5. k_msm_reduce_level    bucket reduction sum (i+1)*S_i as a 32-ary tree of (R, A) pairs
+//   5. k_msm_reduce_level    bucket reduction sum (i+1)*S_i as an 8-ary tree of (R, A) pairs
 //   6. k_msm_window_combine  Horner over the windows (c doublings each), Jacobian result + status word
 //
 // Signed digits halve the bucket count (bucket ids 1..2^(c-1), negative digits add -P).  exp == 0 is skipped
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(32) k_msm_combine_split(const uint32_t *__rest
 // ------------------------------------------------------------------------------------------------ bucket reduction
 // For a range [lo, hi) of buckets: R = sum S_i, A = sum (i - lo) S_i.  A parent over K children of length `len`:
 // R = sum R_j, A = sum A_j + len * sum j R_j (running sum, then log2(len) doublings).  Window sum = A + R.
-static constexpr uint32_t RED_K = 32;
+static constexpr uint32_t RED_K = 8, RED_LOG_K = 3;  // short serial chains per thread: the tree is latency-bound, not work-bound
 template <class F>
 __global__ void __launch_bounds__(64) k_msm_reduce_level(const XYZZ<F> *__restrict__ inR, const XYZZ<F> *__restrict__ inA, uint32_t n_in,
                                                         XYZZ<F> *__restrict__ outR, XYZZ<F> *__restrict__ outA, uint32_t n_out, uint32_t W,
@@ -411,7 +411,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         inR = lr[pp]; inA = la[pp];
         pp ^= 1;
         n_in = n_out;
-        log_len += 5;
+        log_len += RED_LOG_K;
     } while (n_in > 1);
     MsmShape comb = sh;
     comb.W = bw;
