@@ -478,7 +478,7 @@ def bench_spend_proofs(w, zk, rng, world):
     for _ in range(reps):
         prove(w)
     single_ms = (time.perf_counter() - t0) / reps * 1e3
-    streams = 4
+    streams = env_int("B200ZK_SPEND_STREAMS", 8)
     workers = [zk.Worker(w.device) for _ in range(streams)]
     for x in workers:
         prove(x)

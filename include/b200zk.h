@@ -147,7 +147,11 @@ int b200zk_distribute_powers_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, cons
 /* element-wise ops on device vectors of Fr/Fq elements: out[i] = op(a[i], b[i]) (b ignored for unary ops) */
 int b200zk_field_vec_dev(b200zk_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n);
 int b200zk_field_vec(b200zk_ctx *ctx, int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
-/* coeffs[i] *= s (ifft's m^-1 scaling, divide_by_z_on_coset; domain.rs:88-103, 146-159) */
+/* divide_by_z_on_coset (domain.rs:146-159): coeffs[i] *= 1 / (g^m - 1), g = multiplicative_generator() = 7 */
+int b200zk_divide_by_z_on_coset_dev(b200zk_ctx *ctx, void *d_coeffs, uint32_t log_m);
+/* z(tau) = tau^m - 1 (domain.rs:136-141); tau and the result are Montgomery limbs on the host */
+int b200zk_domain_z(b200zk_ctx *ctx, const uint64_t tau[4], uint32_t log_m, uint64_t out[4]);
+/* coeffs[i] *= s (ifft's m^-1 scaling; domain.rs:88-103) */
 int b200zk_fr_scale_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_t s[4]);
 /* point ops on host arrays (parity tests): a = Jacobian points; b = Jacobian (ADD) or affine x||y (ADD_MIXED) */
 int b200zk_point_op(b200zk_ctx *ctx, int group, int op, const uint64_t *a, const uint64_t *b, const uint8_t *b_inf, uint64_t *out, size_t n);

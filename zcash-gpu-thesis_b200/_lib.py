@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200zk_distribute_powers_dev": (_i, [_vp, _vp, _sz, _vp]),
     "b200zk_field_vec_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     "b200zk_field_vec": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
+    "b200zk_divide_by_z_on_coset_dev": (_i, [_vp, _vp, _u32]),
+    "b200zk_domain_z": (_i, [_vp, _vp, _u32, _vp]),
     "b200zk_fr_scale_dev": (_i, [_vp, _vp, _sz, _vp]),
     "b200zk_point_op": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _sz]),
     "b200zk_h_poly": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),

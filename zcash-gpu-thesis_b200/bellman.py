@@ -367,13 +367,16 @@ class EvaluationDomain:
             _raise(self.worker, st)
 
     def z(self, tau: int) -> int:
-        """domain.rs:136-141: tau^m - 1"""
-        return (pow(tau, self.m, FR_MODULUS) - 1) % FR_MODULUS
+        """domain.rs:136-141: tau^m - 1 (computed on the device)"""
+        out = np.zeros(4, dtype=np.uint64)
+        st = self.worker.lib.b200zk_domain_z(self.worker.ctx, _ptr(fr_to_mont_limbs(tau % FR_MODULUS)), self.exp, _ptr(out))
+        if st:
+            _raise(self.worker, st)
+        return fr_from_mont_limbs(out)
 
     def divide_by_z_on_coset(self, worker=None):
-        i = pow(self.z(7), -1, FR_MODULUS)  # multiplicative_generator() = 7 (fr.rs:38-44)
-        il = fr_to_mont_limbs(i)
-        st = self.worker.lib.b200zk_fr_scale_dev(self.worker.ctx, self.buf.ptr, self.m, _ptr(il))
+        """domain.rs:146-159: every coefficient times 1 / z(g), g = multiplicative_generator()"""
+        st = self.worker.lib.b200zk_divide_by_z_on_coset_dev(self.worker.ctx, self.buf.ptr, self.exp)
         if st:
             _raise(self.worker, st)
 

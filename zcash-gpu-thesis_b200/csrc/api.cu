@@ -424,6 +424,25 @@ int b200zk_distribute_powers_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, cons
     return B200ZK_OK;
 }
 
+int b200zk_divide_by_z_on_coset_dev(b200zk_ctx *ctx, void *d_coeffs, uint32_t log_m) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    return ntt_divide_by_z_on_coset(ctx, d_coeffs, log_m);
+}
+
+int b200zk_domain_z(b200zk_ctx *ctx, const uint64_t tau[4], uint32_t log_m, uint64_t out[4]) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    void *d;
+    int rc = stage_small(ctx, tau, &d);
+    if (rc) return rc;
+    rc = ntt_domain_z(ctx, d, log_m, (char *)d + 64);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out, (char *)d + 64, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
 int b200zk_fr_scale_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_t s[4]) {
     CHECK_CTX(ctx);
     USE_DEVICE(ctx);

@@ -84,6 +84,8 @@ int ntt_get_tables(Ctx *ctx, uint32_t log_n, NttTables **out);
 int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind);
 int ntt_distribute_powers(Ctx *ctx, void *d_coeffs, size_t n, const void *d_g);
 void ntt_free_all_tables(Ctx *ctx);
+int ntt_divide_by_z_on_coset(Ctx *ctx, void *d_coeffs, uint32_t log_n);
+int ntt_domain_z(Ctx *ctx, const void *d_tau, uint32_t log_n, void *d_out);
 int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *d_out_repr);
 // msm.cu
 int msm_run(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density,

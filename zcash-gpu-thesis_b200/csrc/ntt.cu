@@ -148,6 +148,19 @@ __global__ void k_into_repr(const fr_t *__restrict__ a, fr_t *__restrict__ out, 
     out[i] = a[i].from_mont();
 }
 
+// divide_by_z_on_coset (domain.rs:146-159): a[i] *= 1 / (g^m - 1), the constant cached with the domain tables
+__global__ void k_scale_by_const(fr_t *__restrict__ a, const fr_t *__restrict__ consts, int which, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[i] = a[i] * consts[which];
+}
+// z(tau) = tau^m - 1 (domain.rs:136-141), one thread
+__global__ void k_domain_z(const fr_t *tau, uint32_t log_m, fr_t *out) {
+    fr_t t = tau[0];
+    for (uint32_t i = 0; i < log_m; i++) t = t.sqr();
+    out[0] = t - fr_t::one();
+}
+
 static void free_tables(NttTables &t) {
     cudaFree(t.tw); cudaFree(t.tw_inv); cudaFree(t.g_lo); cudaFree(t.g_hi); cudaFree(t.gi_lo); cudaFree(t.gi_hi); cudaFree(t.consts);
     t = NttTables();
@@ -234,6 +247,22 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
 int ntt_distribute_powers(Ctx *ctx, void *d_coeffs, size_t n, const void *d_g) {
     if (n == 0) return B200ZK_OK;
     k_distribute_powers<<<(unsigned)((n + 16 * 128 - 1) / (16 * 128)), 128, 0, ctx->stream>>>((fr_t *)d_coeffs, (const fr_t *)d_g, n);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+int ntt_divide_by_z_on_coset(Ctx *ctx, void *d_coeffs, uint32_t log_n) {
+    if (log_n >= 32) return set_error(ctx, B200ZK_ERR_DEGREE_TOO_LARGE, "log_m >= Fr::S (32)");
+    NttTables *t;
+    int st = ntt_get_tables(ctx, log_n, &t);
+    if (st) return st;
+    const size_t n = (size_t)1 << log_n;
+    k_scale_by_const<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((fr_t *)d_coeffs, (const fr_t *)t->consts, C_Z_INV, n);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+int ntt_domain_z(Ctx *ctx, const void *d_tau, uint32_t log_n, void *d_out) {
+    k_domain_z<<<1, 1, 0, ctx->stream>>>((const fr_t *)d_tau, log_n, (fr_t *)d_out);
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
