@@ -398,7 +398,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
     k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
                                                                                   task_cnt, task_off, order, cap, buckets, partials);
-    k_msm_combine_split<F><<<256, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
+    k_msm_combine_split<F><<<2048, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
     // reduction tree
     const XYZZ<F> *inR = buckets, *inA = nullptr;
