@@ -184,6 +184,8 @@ int b200zk_groth16_prove(b200zk_ctx *ctx, const b200zk_crs *crs, const uint64_t 
 /* Per-kernel timing for the roofline report: when enabled, b200zk_multiexp(_dev) brackets its dominant kernel
  * (bucket accumulation) with CUDA events on the context's stream; read() synchronises and returns the summed
  * milliseconds and the number of launches since the last read. */
+/* Kernels launched on this context by multiexp / ntt / h_poly / groth16_prove since creation (or the last reset). */
+unsigned long long b200zk_launch_count(b200zk_ctx *ctx, int reset);
 int b200zk_profile_enable(b200zk_ctx *ctx, int on);
 int b200zk_profile_read(b200zk_ctx *ctx, double *accumulate_ms, int *launches);
 

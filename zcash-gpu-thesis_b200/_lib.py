@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200zk_crs_create": (_i, [_vp] * 12 + [C.POINTER(_vp)]),
     "b200zk_crs_free": (None, [_vp]),
     "b200zk_groth16_prove": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200zk_launch_count": (C.c_ulonglong, [_vp, _i]),
     "b200zk_profile_enable": (_i, [_vp, _i]),
     "b200zk_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),
     "b200zk_microbench": (_i, [_vp, _i, _i, C.POINTER(C.c_double)]),

@@ -588,6 +588,13 @@ int b200zk_groth16_prove(b200zk_ctx *ctx, const b200zk_crs *crs, const uint64_t 
     return groth16_prove(ctx, crs, g, proof_a, proof_b, proof_c, inf_flags);
 }
 
+unsigned long long b200zk_launch_count(b200zk_ctx *ctx, int reset) {
+    if (!ctx) return 0;
+    unsigned long long v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
 int b200zk_profile_enable(b200zk_ctx *ctx, int on) {
     CHECK_CTX(ctx);
     ctx->prof_on = on != 0;

@@ -180,6 +180,7 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     const g2_affine_t *vk2 = (const g2_affine_t *)((const char *)crs->vk + 3 * 96);
     g1_jac_t *mid = (g1_jac_t *)(w + o_mid), *prod = (g1_jac_t *)(w + o_prod);
     uint8_t *dinf = (uint8_t *)(w + o_inf);
+    ctx->launches += 3;
     k_proof_stage1<<<2, 32, 32 * sizeof(g2_xyzz_t), st>>>((const g1_xyzz_t *)crs->table_delta_g1, (const g2_xyzz_t *)crs->table_delta_g2,
                                                          (const uint32_t *)(w + o_scal), vk1, vk2, r1, r2, mid, (g2_affine_t *)(w + o_pb), dinf);
     k_proof_stage2<<<2, 32, 0, st>>>(mid, (const uint32_t *)(w + o_scal), prod);

@@ -100,13 +100,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const T *__restrict
 }
 // out[i] = exclusive prefix of in; out[n] (and *total) = sum.  `sums` needs ceil(n / SCAN_BLOCK) + 1 words.
 template <class T>
-static void scan_u32(cudaStream_t st, const T *in, size_t n, uint32_t *out, uint32_t *out2, uint32_t *sums) {
-    if (n == 0) { cudaMemsetAsync(out, 0, sizeof(uint32_t), st); if (out2) cudaMemsetAsync(out2, 0, sizeof(uint32_t), st); return; }
+static int scan_u32(cudaStream_t st, const T *in, size_t n, uint32_t *out, uint32_t *out2, uint32_t *sums) {
+    if (n == 0) { cudaMemsetAsync(out, 0, sizeof(uint32_t), st); if (out2) cudaMemsetAsync(out2, 0, sizeof(uint32_t), st); return 0; }
     size_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     k_scan_block_sums<T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums);
     k_scan_sums<<<1, 1024, 0, st>>>(sums, nb, out + n);
     k_scan_apply<T><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums, out, out2);
     if (out2) cudaMemcpyAsync(out2 + n, out + n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+    return 3;
 }
 
 // ------------------------------------------------------------------------------------------------ digits / sort
@@ -380,11 +381,11 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         return B200ZK_OK;
     }
     B200ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (nbk + 1) * sizeof(uint32_t), st));
-    if (d_density) scan_u32<uint8_t>(st, d_density, n_exp, rank, nullptr, sums);
+    if (d_density) ctx->launches += scan_u32<uint8_t>(st, d_density, n_exp, rank, nullptr, sums);
     const unsigned eb = (unsigned)((n_exp + 255) / 256);
     k_msm_digits<0><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, counts,
                                         nullptr, status);
-    scan_u32<uint32_t>(st, counts, nbk, offsets, cursor, sums);
+    ctx->launches += scan_u32<uint32_t>(st, counts, nbk, offsets, cursor, sums);
     k_msm_digits<1><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, cursor,
                                         sorted, status);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -393,8 +394,9 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, sizeof(uint32_t), st));
     B200ZK_CUDA(ctx, cudaMemsetAsync(size_hist, 0, (cap + 2) * sizeof(uint32_t), st));
     k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split, size_hist);
-    scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
-    scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
+    ctx->launches += scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
+    ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
+    ctx->launches += 7;  // digits x2, count_tasks, order_buckets, accumulate, combine_split, window_combine
     k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
     k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
                                                                                   task_cnt, task_off, order, cap, buckets, partials);
@@ -408,6 +410,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         uint32_t n_out = (n_in + RED_K - 1) / RED_K;
         uint32_t threads = n_out * bw;
         k_msm_reduce_level<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, n_in, lr[pp], la[pp], n_out, bw, log_len);
+        ctx->launches++;
         inR = lr[pp]; inA = la[pp];
         pp ^= 1;
         n_in = n_out;

@@ -237,6 +237,7 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         size_t smem = (size_t)8 * sizeof(uint32_t) << T;
         unsigned tiles = (unsigned)(n >> T);
         k_ntt_pass<<<tiles, NTT_THREADS, smem, ctx->stream>>>(src, dst, tw, lo, hi, (const fr_t *)t->consts, p);
+        ctx->launches++;
         s0 += p.B;
     }
     if (npass == 1) B200ZK_CUDA(ctx, cudaMemcpyAsync(A, S, n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -277,6 +278,7 @@ int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *
     }
     NttTables *t;
     if ((st = ntt_get_tables(ctx, log_n, &t))) return st;
+    ctx->launches += 2;
     k_h_combine<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((fr_t *)d_a, (const fr_t *)d_b, (const fr_t *)d_c, (const fr_t *)t->consts, n);
     if ((st = ntt_run(ctx, d_a, log_n, B200ZK_ICOSET_FFT))) return st;
     if (n > 1) k_into_repr<<<(unsigned)((n - 1 + 255) / 256), 256, 0, ctx->stream>>>((const fr_t *)d_a, (fr_t *)d_out_repr, n - 1);
