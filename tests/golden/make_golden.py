@@ -7,6 +7,7 @@ Sources (all under /root/reference/librustzcash):
   pairing/src/bls12_381/fq.rs:2558-2584, 2630-2651     Fq mul / square KATs
   pairing/src/bls12_381/ec.rs:1060-1175                G1 add / double KATs (canonical coordinates)
   pairing/src/bls12_381/tests/*.dat                    1000 multiples of the generators, 4 encodings
+  pairing/src/bls12_381/tests/mod.rs:5-53              pairing KAT e(G1, G2) (RELIC)
   bellman/src/groth16/tests/mod.rs:98-400              test_xordemo constants (DummyEngine, Fr = Z/64513)
 Only literal test constants are extracted (no source code is copied).
 """
@@ -57,6 +58,11 @@ def main():
         dat[name] = {"entry_bytes": sz, "entries": 1000, "sha256": hashlib.sha256(b).hexdigest(),
                      "first": [b[i * sz:(i + 1) * sz].hex() for i in range(4)], "last": b[999 * sz:].hex()}
     out["dat"] = dat
+    src = open(os.path.join(REF, "pairing/src/bls12_381/tests/mod.rs")).read().split("\n")[20:55]
+    vals = re.findall(r'from_str\("(\d+)"\)', "\n".join(src))
+    assert len(vals) == 12
+    out["pairing_g1_g2"] = {"src": "pairing/src/bls12_381/tests/mod.rs:5-53 (RELIC): e(G1::one(), G2::one()) as c0.c0.c0, c0.c0.c1, c0.c1.c0, ... decimal",
+                            "fq12": vals}
     out["xordemo"] = {
         "src": "bellman/src/groth16/tests/mod.rs:98-400 + tests/dummy_engine.rs (Fr = Z/64513, generator 5, S = 10)",
         "modulus": 64513, "generator": 5, "s": 10, "root_2_10": 57751, "root_2_3": 20201,

@@ -11,10 +11,8 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-class BlsEngine:
-    Fr = Fr
-    G1 = G1
-    G2 = G2
+from oracle.pairing import Bls12 as BlsEngine  # Fr, G1, G2 + the pairing check of verify_proof
+from oracle.groth16 import Proof as OracleProof, verify_proof
 
 
 class MiMCLike(Circuit):
@@ -109,10 +107,13 @@ def test_create_proof_matches_oracle(worker, which):
         assert _same_point(G1, got.c, got.inf[2], want.c)
         assert got.write(worker) == proof_bytes(want)
         assert len(got.write(worker)) == 192  # groth16/mod.rs:567
-    # the proof satisfies the Groth16 equation in the exponent (toxic waste known): A*B = alpha*beta + acc*gamma + C*delta
-    alpha, beta, gamma, delta, tau = toxic
-    # recover discrete logs through the oracle pipeline on the DummyEngine-like scalar model is not possible for BLS points;
-    # the pairing-free consistency check is the equality with the oracle proof above plus the oracle's own xordemo KAT.
+    # the GPU proof verifies under the real pairing check (verifier.rs:35-66) and fails for a wrong public input
+    aff = lambda G, limbs, inf: G.affine_zero() if inf else tuple(
+        [G.F.from_mont_limbs(list(map(int, limbs[: len(limbs) // 2]))), G.F.from_mont_limbs(list(map(int, limbs[len(limbs) // 2:]))), False])
+    gp = OracleProof(a=aff(G1, got.a, got.inf[0]), b=aff(G2, got.b, got.inf[1]), c=aff(G1, got.c, got.inf[2]))
+    public = asg.input_assignment[1:]
+    assert verify_proof(E, params.vk, gp, public)
+    assert not verify_proof(E, params.vk, gp, [(public[0] + 1) % Fr.p] + public[1:])
 
 
 def test_subversion_check(worker):

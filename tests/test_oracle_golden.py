@@ -241,3 +241,32 @@ def test_h_poly_cpp_matches_python():
     want = domain.h_coefficients(Fr, *[[Fr.from_mont_limbs(x) for x in v] for v in (a, b, c)])
     got = cref.h_poly(a, b, c)
     assert [limbs_to_int(x) for x in got] == want
+
+
+def test_pairing_kat_and_groth16_verify():
+    """pairing/src/bls12_381/tests/mod.rs:5-53: e(G1, G2) equals the RELIC value; bilinearity; and the oracle's BLS12-381
+    Groth16 round trip (groth16/mod.rs:493-575 MySillyCircuit: prove, verify true, wrong public input verifies false)."""
+    from oracle import pairing as pr
+    from oracle.groth16 import verify_proof
+
+    e = pr.pairing(G1.gen, G2.gen)
+    assert pr.f12_flat(e) == [int(v) for v in KAT["pairing_g1_g2"]["fq12"]]
+    a, b = 0x1234567, 0x7654321
+    lhs = pr.pairing(G1.into_affine(G1.mul(G1.gen, a)), G2.into_affine(G2.mul(G2.gen, b)))
+    assert lhs == pr.f12_pow(e, a * b % Fr.p)
+
+    class Silly(Circuit):
+        def __init__(self, a, b):
+            self.a, self.b = a, b
+
+        def synthesize(self, cs):
+            x = cs.alloc(lambda: self.a)
+            y = cs.alloc(lambda: self.b)
+            z = cs.alloc_input(lambda: self.a * self.b % Fr.p)
+            cs.enforce([(x, 1)], [(y, 1)], [(z, 1)])
+
+    E = pr.Bls12
+    params, _ = generate_parameters(E, Silly(0, 0), G1.gen, G2.gen, 1111, 2222, 3333, 4444, 5555)
+    proof = create_proof(E, Silly(6, 7), params, 99, 101)
+    assert verify_proof(E, params.vk, proof, [42])
+    assert not verify_proof(E, params.vk, proof, [43])
