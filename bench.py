@@ -308,10 +308,41 @@ def main():
     ms_step = ms_total / args.steps
     value = world * n / (ms_step * 1e-3)
 
-    # ---- timed: e2e through the host-buffer entry point
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    # ---- timed: e2e through the host-buffer entry point.  World 1: the reference's future-returning multiexp(): step k + 1 is
+    # submitted before step k is waited for (the prover keeps its multiexps in flight, prover.rs:289-354), so the H2D copy of
+    # the next exponents overlaps the running multiexp; every step still copies its 512 MiB of exponents from pinned host
+    # memory and reads its result back inside the timed region.
+    def run_e2e(steps):
+        if world > 1:
+            for _ in range(steps):
+                step_e2e()
+            return
+        pend = None
+        for _ in range(steps):
+            job = ctypes.c_void_p()
+            st = lib.b200zk_multiexp_async(w.ctx, bases.handle, 0, pinned.ctypes.data_as(ctypes.c_void_p), n, None, ctypes.byref(job))
+            assert st == 0, w.last_error()
+            if pend is not None:
+                assert lib.b200zk_job_wait(pend, out_host.ctypes.data_as(ctypes.c_void_p)) == 0, w.last_error()
+            pend = job
+        assert lib.b200zk_job_wait(pend, out_host.ctypes.data_as(ctypes.c_void_p)) == 0, w.last_error()
+
+    step_e2e()
+    if world == 1:
+        ref_out = out_host.copy()
+        run_e2e(2)
+        assert np.array_equal(zk.into_affine(w, zk.G1, out_host)[0], zk.into_affine(w, zk.G1, ref_out)[0])
+    barrier()
+    t0 = time.perf_counter()
+    w.timer_start()
+    run_e2e(args.steps)
+    e2e_dev_ms = w.timer_stop()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    tt = torch.tensor([max(e2e_dev_ms, e2e_wall_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_ms = float(tt.item()) / args.steps
     e2e_value = world * n / (e2e_ms * 1e-3)
 
     # ---- roofline for the dominant kernel (bucket accumulation), integer pipe
@@ -373,7 +404,8 @@ def main():
                                                                         "one_time_setup_s": t_pre}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(scalars.nbytes), "d2h_bytes_per_step": 148,
-                    "note": "b200zk_multiexp with pinned host scalars; bases (the CRS) stay resident"},
+                    "note": "b200zk_multiexp_async / b200zk_job_wait (the future-returning multiexp of the reference, depth-2 pipeline) with pinned host "
+                            "scalars; bases (the CRS) stay resident; time = max(device events, host wall clock) over the steps"},
             "gpu_launches": launches_timed + (2 * args.steps if world > 1 else 0),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -114,6 +114,15 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
  * synchronous call's return value; pass NULL to ignore. */
 int b200zk_multiexp_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp,
                         const uint8_t *d_density, void *d_out_jacobian, void *d_status);
+/* The reference's multiexp() returns a future and the prover keeps several in flight (prover.rs:289-318, 339-354).
+ * _async enqueues the host->device copy of the exponents on the context's copy stream and the multiexp behind it on the
+ * compute stream, then returns; copies of later jobs overlap the computation of earlier ones.  `scalars` / `density` must
+ * stay valid (and should be pinned) until b200zk_job_wait, which blocks, writes the Jacobian result, returns the same status
+ * codes as b200zk_multiexp and releases the job.  Jobs of one context complete in submission order. */
+typedef struct b200zk_job b200zk_job;
+int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                          const uint8_t *density, b200zk_job **job);
+int b200zk_job_wait(b200zk_job *job, uint64_t *out_jacobian);
 /* Pippenger window override for tuning (0 = automatic). */
 int b200zk_set_msm_window(b200zk_ctx *ctx, int window_bits);
 

@@ -100,6 +100,32 @@ auto multiexp(const Worker &pool, std::pair<const Bases<GROUP> *, size_t> bases,
     return multiexp<GROUP>(pool, bases, static_cast<const DensityTracker *>(nullptr), exponents);
 }
 
+// The future multiexp() returns in the reference (`Box<Future<Item = G::Projective, Error = SynthesisError>>`): submit now,
+// wait() later; several may be in flight per Worker (prover.rs:289-318, 339-354).  The exponent vector must outlive wait().
+template <int GROUP>
+class MultiexpFuture {
+public:
+    typedef typename std::conditional<GROUP == B200ZK_G1, G1Projective, G2Projective>::type Projective;
+    MultiexpFuture(const Worker &pool, std::pair<const Bases<GROUP> *, size_t> bases, const DensityTracker *density_map, const std::vector<FrRepr> &exponents)
+        : pool_(pool) {
+        if (density_map && density_map->bv.size() != exponents.size()) throw std::logic_error("query_size == exponents.len()");
+        pool.check(b200zk_multiexp_async(pool.ctx(), bases.first->handle(), bases.second, exponents.empty() ? nullptr : exponents[0].data(),
+                                         exponents.size(), density_map ? density_map->bv.data() : nullptr, &job_));
+    }
+    MultiexpFuture(MultiexpFuture &&o) noexcept : pool_(o.pool_), job_(o.job_) { o.job_ = nullptr; }
+    ~MultiexpFuture() { if (job_) b200zk_job_wait(job_, nullptr); }
+    Projective wait() {
+        Projective out{};
+        b200zk_job *j = job_;
+        job_ = nullptr;
+        pool_.check(b200zk_job_wait(j, out.data()));
+        return out;
+    }
+private:
+    const Worker &pool_;
+    b200zk_job *job_ = nullptr;
+};
+
 // bellman::domain::EvaluationDomain<E, Scalar<E>> with the coefficients resident on the GPU
 class EvaluationDomain {
 public:

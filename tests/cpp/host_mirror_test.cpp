@@ -78,6 +78,14 @@ int main() {
     } catch (const SynthesisError &e) {
         CHECK(e.kind == SynthesisError::IoErrorUnexpectedEof);
     }
+    // futures: two multiexps in flight, waited for later (prover.rs:289-318, 339-354)
+    {
+        std::vector<FrRepr> e1{FrRepr{2, 0, 0, 0}, FrRepr{3, 0, 0, 0}}, e2{FrRepr{5, 0, 0, 0}};
+        MultiexpFuture<B200ZK_G1> f1(w, {&bases, 0}, nullptr, e1), f2(w, {&bases, 1}, nullptr, e2);
+        auto a1 = to_affine(w, f1.wait(), &i1);
+        auto a2 = to_affine(w, f2.wait(), &i2);
+        CHECK(a1 == a2 && !i1 && !i2);
+    }
     // precomputed tables do not change the result
     bases.precompute(8);
     auto r23p = multiexp<B200ZK_G1>(w, {&bases, 0}, FullDensity(), std::vector<FrRepr>{FrRepr{2, 0, 0, 0}, FrRepr{3, 0, 0, 0}});

@@ -272,3 +272,33 @@ def test_witness_like_scalars_split_buckets(worker):
     aff, inf = _check(worker, "g1", xy, exps)
     want_xy, want_inf = util.affine_of_scalar("g1", util.expected_scalar(ks, exps))
     assert inf == want_inf and np.array_equal(aff, want_xy)
+
+
+def test_multiexp_futures_in_flight(worker):
+    """multiexp() returns a future and the prover keeps several in flight (prover.rs:289-318, 339-354): results equal the
+    synchronous call, errors surface at wait()."""
+    import zcash_gpu_thesis_b200 as zk
+
+    n = 3000
+    r = util.rng(1500)
+    xy, ks = util.random_bases("g1", r, n)
+    bases = zk.Bases(worker, zk.G1, xy)
+    exps = [util.random_fr_repr(r, n) for _ in range(4)]
+    density = zk.DensityTracker((r.random(n) < 0.5))
+    futs = [zk.multiexp_async(worker, (bases, 0), zk.FullDensity() if i % 2 == 0 else density, e) for i, e in enumerate(exps)]
+    for i, (f, e) in enumerate(zip(futs, exps)):
+        got = f.wait()
+        want = zk.multiexp(worker, (bases, 0), zk.FullDensity() if i % 2 == 0 else density, e)
+        assert np.array_equal(zk.into_affine(worker, zk.G1, got)[0], zk.into_affine(worker, zk.G1, want)[0])
+    short = zk.Bases(worker, zk.G1, xy[:100])
+    f_ok = zk.multiexp_async(worker, (bases, 0), zk.FullDensity(), exps[0])
+    f_bad = zk.multiexp_async(worker, (short, 0), zk.FullDensity(), exps[1])
+    f_ok.wait()
+    with pytest.raises(zk.IoError):
+        f_bad.wait()
+    # a fifth job while four are pending is refused, not queued silently
+    pend = [zk.multiexp_async(worker, (bases, 0), zk.FullDensity(), exps[0]) for _ in range(4)]
+    with pytest.raises(ValueError):
+        zk.multiexp_async(worker, (bases, 0), zk.FullDensity(), exps[0])
+    for f in pend:
+        f.wait()

@@ -27,6 +27,7 @@ from .bellman import (  # noqa: F401
     h_poly,
     into_affine,
     multiexp,
+    multiexp_async,
     ntt_host,
     point_op,
 )

@@ -300,6 +300,41 @@ def multiexp(pool: Worker, bases, density_map, exponents):
     return out
 
 
+class MultiexpFuture:
+    """The `Box<Future<Item = G::Projective, Error = SynthesisError>>` that multiexp returns (multiexp.rs:285-295)."""
+
+    def __init__(self, pool, job, group, keep):
+        self.pool, self.job, self.group, self.keep = pool, job, group, keep
+
+    def wait(self):
+        out = np.zeros(18 if self.group == L.G1 else 36, dtype=np.uint64)
+        st = self.pool.lib.b200zk_job_wait(self.job, _ptr(out))
+        self.job, self.keep = None, None
+        if st:
+            _raise(self.pool, st)
+        return out
+
+
+def multiexp_async(pool: Worker, bases, density_map, exponents) -> MultiexpFuture:
+    """multiexp() as the reference uses it: returns immediately with a future; several may be in flight per Worker
+    (prover.rs:289-318).  `exponents` should live in pinned memory for the copy to overlap the previous job."""
+    if isinstance(bases, tuple):
+        bases, offset = bases
+    else:
+        offset = 0
+    exponents = _u64(exponents, 4)
+    n = exponents.shape[0]
+    density = None
+    if density_map is not None and density_map.get_query_size() is not None:
+        assert density_map.get_query_size() == n
+        density = density_map.as_bytes()
+    job = C.c_void_p()
+    st = pool.lib.b200zk_multiexp_async(pool.ctx, bases.handle, offset, _ptr(exponents), n, _ptr(density), C.byref(job))
+    if st:
+        _raise(pool, st)
+    return MultiexpFuture(pool, job, bases.group, (exponents, density))
+
+
 def into_affine(pool: Worker, group: int, jacobian):
     """CurveProjective::into_affine (ec.rs:586-619) on the device. Returns (xy array (n, 12|24), infinity flags)."""
     w = 18 if group == L.G1 else 36

@@ -72,6 +72,7 @@ using namespace b200zk;
 struct b200zk_ctx : public Ctx {};
 struct b200zk_bases : public Bases {};
 struct b200zk_crs : public Crs {};
+struct b200zk_job { b200zk_ctx *ctx; int slot; int group; size_t o_res, o_st; };
 
 #define CHECK_CTX(ctx) do { if (!(ctx)) return B200ZK_ERR_BAD_ARG; } while (0)
 #define USE_DEVICE(ctx) B200ZK_CUDA(ctx, cudaSetDevice((ctx)->device))
@@ -114,6 +115,8 @@ void b200zk_destroy(b200zk_ctx *ctx) {
     cudaFree(ctx->scratch);
     cudaFree(ctx->scratch2);
     cudaFree(ctx->scratch3);
+    for (auto &sl : ctx->slots) { cudaFree(sl.dev); if (sl.host_res) cudaFreeHost(sl.host_res); if (sl.copied) cudaEventDestroy(sl.copied); if (sl.done) cudaEventDestroy(sl.done); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -302,6 +305,61 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
     B200ZK_CUDA(ctx, cudaMemcpyAsync(out_jacobian, s + o_res, jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(&status, s + o_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status, "UnexpectedIdentity: a base at infinity was consumed");
+    if (status == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status, "IoError(UnexpectedEof): expected more bases from source");
+    return B200ZK_OK;
+}
+
+int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                          const uint8_t *density, b200zk_job **job) {
+    CHECK_CTX(ctx);
+    if (!bases || !job || (n_exp && !scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    USE_DEVICE(ctx);
+    if (!ctx->copy_stream) B200ZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    int si = -1;
+    for (int i = 0; i < 4; i++) if (!ctx->slots[i].busy) { si = i; break; }
+    if (si < 0) return set_error(ctx, B200ZK_ERR_BAD_ARG, "too many multiexp jobs in flight on this context (max 4): wait for one first");
+    Ctx::JobSlot &sl = ctx->slots[si];
+    const size_t sc_bytes = n_exp * 32, den_bytes = density ? n_exp : 0;
+    const size_t o_den = (sc_bytes + 255) / 256 * 256, o_res = o_den + (den_bytes + 255) / 256 * 256, o_st = o_res + 512, total = o_st + 256;
+    if (sl.bytes < total) {
+        if (sl.dev) { B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); B200ZK_CUDA(ctx, cudaFree(sl.dev)); sl.dev = nullptr; sl.bytes = 0; }
+        B200ZK_CUDA(ctx, cudaMalloc(&sl.dev, total));
+        sl.bytes = total;
+    }
+    if (!sl.host_res) {
+        B200ZK_CUDA(ctx, cudaMallocHost(&sl.host_res, 512));
+        B200ZK_CUDA(ctx, cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+        B200ZK_CUDA(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    char *d = (char *)sl.dev;
+    if (sc_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(d, scalars, sc_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (den_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(d + o_den, density, den_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    B200ZK_CUDA(ctx, cudaEventRecord(sl.copied, ctx->copy_stream));
+    B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
+    int rc = msm_run(ctx, bases, base_offset, d, n_exp, density ? (const uint8_t *)(d + o_den) : nullptr, d + o_res, d + o_st, g_window_override);
+    if (rc) return rc;
+    const size_t jac_bytes = bases->group == B200ZK_G1 ? 144 : 288;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(sl.host_res, d + o_res, jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync((char *)sl.host_res + 320, d + o_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
+    sl.busy = true;
+    b200zk_job *j = new b200zk_job{ctx, si, bases->group, o_res, o_st};
+    *job = j;
+    return B200ZK_OK;
+}
+
+int b200zk_job_wait(b200zk_job *job, uint64_t *out_jacobian) {
+    if (!job) return B200ZK_ERR_BAD_ARG;
+    b200zk_ctx *ctx = job->ctx;
+    Ctx::JobSlot &sl = ctx->slots[job->slot];
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaEventSynchronize(sl.done);
+    uint32_t status = *(const uint32_t *)((const char *)sl.host_res + 320);
+    if (e == cudaSuccess && out_jacobian) memcpy(out_jacobian, sl.host_res, job->group == B200ZK_G1 ? 144 : 288);
+    sl.busy = false;
+    delete job;
+    if (e != cudaSuccess) return set_error(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status, "UnexpectedIdentity: a base at infinity was consumed");
     if (status == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status, "IoError(UnexpectedEof): expected more bases from source");
     return B200ZK_OK;

@@ -57,6 +57,9 @@ struct Ctx {
     int rank = 0, world = 1;
     void *gather_buf = nullptr;  // world * 288 B
     void *small_slot = nullptr;  // 256 B staging for scalar constants
+    cudaStream_t copy_stream = nullptr;  // H2D of the next job's exponents while the current one computes
+    struct JobSlot { void *dev = nullptr; size_t bytes = 0; void *host_res = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool busy = false; };
+    JobSlot slots[4];
     unsigned long long launches = 0;  // kernels launched by this context (b200zk_launch_count)
     bool prof_on = false;        // bracket the dominant MSM kernel with events
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
