@@ -17,6 +17,9 @@
 
 namespace b200zk {
 
+// -p^-1 mod 2^32 for Fr and Fq, read at run time (see mad_n_redc)
+__device__ __constant__ uint32_t B200ZK_M0_RT[2] = {0xffffffffu, 0xfffcfffdu};
+
 // ------------------------------------------------------------------------------------------------ PTX carry helpers
 __device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -163,8 +166,17 @@ struct __align__(16) Fp {
     // same with the modulus (immediates); `odd` selects limbs 1,3,5.. of p
     template <int ODD>
     __device__ __forceinline__ static void cmad_mod(uint32_t *acc, uint32_t mi) {
-        acc[0] = mad_lo_cc(P::mod(ODD), mi, acc[0]);
-        acc[1] = madc_hi_cc(P::mod(ODD), mi, acc[1]);
+        if (P::mod(0) == 1u && P::mod(1) == 0xffffffffu) {
+            // Fr: the two low limbs of r are 1 and 2^32 - 1, so their products with m need no multiplier:
+            //   m * 1 = m ;  m * (2^32 - 1) = (m - [m != 0]) * 2^32 + (2^32 - m)   (hi : lo)
+            uint32_t lo = ODD ? 0u - mi : mi;
+            uint32_t hi = ODD ? mi - (mi != 0u) : 0u;
+            acc[0] = add_cc(acc[0], lo);
+            acc[1] = addc_cc(acc[1], hi);
+        } else {
+            acc[0] = mad_lo_cc(P::mod(ODD), mi, acc[0]);
+            acc[1] = madc_hi_cc(P::mod(ODD), mi, acc[1]);
+        }
 #pragma unroll
         for (int j = 2; j < N; j += 2) { acc[j] = madc_lo_cc(P::mod(j + ODD), mi, acc[j]); acc[j + 1] = madc_hi_cc(P::mod(j + ODD), mi, acc[j + 1]); }
     }
@@ -192,7 +204,9 @@ struct __align__(16) Fp {
             cmad_n(even, a, bi);
             odd[N - 1] = addc(odd[N - 1], 0);
         }
-        uint32_t mi = even[0] * P::M0;
+        // M0 comes from constant memory: for Fr it is 2^32 - 1 and ptxas would otherwise rewrite m = -t0 and the
+        // m * p_k products into negated IMAD.X / IMAD.HI pairs (6 cycles) instead of one IMAD.WIDE.X (4 cycles)
+        uint32_t mi = even[0] * B200ZK_M0_RT[P::N == 8 ? 0 : 1];
         cmad_mod<1>(odd, mi);
         cmad_mod<0>(even, mi);
         odd[N - 1] = addc(odd[N - 1], 0);

@@ -78,7 +78,7 @@ __device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t tile, uint32_t e
     for (int l = 0; l < 8; l++) sm[l * tile + e] = x.v[l];
 }
 
-__global__ void __launch_bounds__(NTT_THREADS) k_ntt_pass(const fr_t *__restrict__ in, fr_t *__restrict__ out, const fr_t *__restrict__ tw,
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_ntt_pass(const fr_t *__restrict__ in, fr_t *__restrict__ out, const fr_t *__restrict__ tw,
                                                          const fr_t *__restrict__ sc_lo, const fr_t *__restrict__ sc_hi,
                                                          const fr_t *__restrict__ consts, NttPass p) {
     extern __shared__ uint32_t sm[];
