@@ -368,7 +368,7 @@ def main():
     roofline = {
         "kernel": "k_msm_accumulate<fq_t>", "bound": "int32",
         "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "TIMAD/s", "frac": achieved / int_peak if int_peak else None,
-        "traffic": None,
+        "traffic": traffic_from_profile(),
         "note": "MSM is bound by the INT32 multiplier pipe (no dense contraction, HBM-light): achieved = algorithmic 32x32->64 multiply-adds of "
                 "the reference algorithm (3300*W(n) per point, W(2^24)=15 windows of c=17; SURVEY.md 8d) / measured accumulate-kernel time; peak = "
                 "32 IMAD.WIDE/clk/SM x SMs x sampled SM clock (the fmaheavy pipe rate established with ncu); the 64/clk/SM figure of plain 32-bit "
@@ -415,6 +415,16 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def traffic_from_profile():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/r01_traffic.json); None when the capture does not match the precomputed-table configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"], "workload": t["workload"]}
+    except Exception:
+        return None
 
 
 def bench_extra(w, zk, lib, rng, timed, world):

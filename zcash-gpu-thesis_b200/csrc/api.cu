@@ -268,11 +268,10 @@ void b200zk_bases_free(b200zk_bases *bases) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------- multiexp
-static int g_window_override = 0;
 int b200zk_set_msm_window(b200zk_ctx *ctx, int window_bits) {
     CHECK_CTX(ctx);
     if (window_bits != 0 && (window_bits < 2 || window_bits > 24)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "window bits must be 0 or in [2, 24]");
-    g_window_override = window_bits;
+    ctx->window_override = window_bits;
     return B200ZK_OK;
 }
 
@@ -282,7 +281,7 @@ int b200zk_multiexp_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_
     if (!bases || !d_out_jacobian || (n_exp && !d_scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
     if (bases->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bases live on another device");
     USE_DEVICE(ctx);
-    return msm_run(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jacobian, d_status, g_window_override);
+    return msm_run(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jacobian, d_status, ctx->window_override);
 }
 
 int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
@@ -299,7 +298,7 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
     char *s = (char *)ctx->scratch;
     if (sc_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(s, scalars, sc_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (den_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(s + o_den, density, den_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = msm_run(ctx, bases, base_offset, s, n_exp, density ? (const uint8_t *)(s + o_den) : nullptr, s + o_res, s + o_st, g_window_override);
+    rc = msm_run(ctx, bases, base_offset, s, n_exp, density ? (const uint8_t *)(s + o_den) : nullptr, s + o_res, s + o_st, ctx->window_override);
     if (rc) return rc;
     uint32_t status = 0;
     B200ZK_CUDA(ctx, cudaMemcpyAsync(out_jacobian, s + o_res, jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -337,7 +336,7 @@ int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t bas
     if (den_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(d + o_den, density, den_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     B200ZK_CUDA(ctx, cudaEventRecord(sl.copied, ctx->copy_stream));
     B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
-    int rc = msm_run(ctx, bases, base_offset, d, n_exp, density ? (const uint8_t *)(d + o_den) : nullptr, d + o_res, d + o_st, g_window_override);
+    int rc = msm_run(ctx, bases, base_offset, d, n_exp, density ? (const uint8_t *)(d + o_den) : nullptr, d + o_res, d + o_st, ctx->window_override);
     if (rc) return rc;
     const size_t jac_bytes = bases->group == B200ZK_G1 ? 144 : 288;
     B200ZK_CUDA(ctx, cudaMemcpyAsync(sl.host_res, d + o_res, jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));

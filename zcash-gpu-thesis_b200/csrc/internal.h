@@ -60,6 +60,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;  // H2D of the next job's exponents while the current one computes
     struct JobSlot { void *dev = nullptr; size_t bytes = 0; void *host_res = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool busy = false; };
     JobSlot slots[4];
+    int window_override = 0;  // b200zk_set_msm_window
     unsigned long long launches = 0;  // kernels launched by this context (b200zk_launch_count)
     bool prof_on = false;        // bracket the dominant MSM kernel with events
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
