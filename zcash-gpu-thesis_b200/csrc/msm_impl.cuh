@@ -193,7 +193,7 @@ static __global__ void k_msm_order_buckets(const uint32_t *__restrict__ offsets,
 }
 
 template <class F>
-__global__ void __launch_bounds__(128, B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128, sizeof(F) > 48 ? 2 : B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                        const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
                                                        const uint32_t *__restrict__ task_off, const uint32_t *__restrict__ order, uint32_t cap,
                                                        XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ partials) {
@@ -283,6 +283,57 @@ __global__ void __launch_bounds__(64) k_msm_reduce_level(const XYZZ<F> *__restri
     outA[t] = accw;
 }
 
+// ---- bit-sliced tail of the bucket reduction --------------------------------------------------------------------------
+// Once a window is down to n <= SLICE_MAX entries (R_i, A_i) the 8-ary tree would still cost ~30 serial point operations
+// per level; a single thread needs ~10 us per point addition, so small multiexps (a Sapling proof's are ~10^5 points) were
+// spending most of their time here.  sum_i i R_i = sum_j 2^j T_j with T_j = sum over {i : bit j of i} R_i: all T_j, sum R_i and
+// sum A_i are plain sums, computed together by log8(n) levels of <= 8 additions (k_msm_slice_sum), then one short Horner.
+static constexpr uint32_t SLICE_MAX = 32768;
+// slice s < nb: masked sum of R (bit s of the index); s == nb: sum of R; s == nb + 1: sum of A.
+// first level: in = R / A arrays of n_in entries per window; later levels: in = previous Y ((nb + 2) rows of n_in per window)
+template <class F>
+__global__ void __launch_bounds__(64) k_msm_slice_sum(const XYZZ<F> *__restrict__ R, const XYZZ<F> *__restrict__ A, const XYZZ<F> *__restrict__ Yin,
+                                                     uint32_t n_in, uint32_t nb, uint32_t n_out, uint32_t W, XYZZ<F> *__restrict__ Yout) {
+    const uint32_t S = nb + 2;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * S * n_out) return;
+    uint32_t c = t % n_out, s = (t / n_out) % S, w = t / (n_out * S);
+    uint32_t first = c * 8, last = min(first + 8, n_in);
+    XYZZ<F> acc = XYZZ<F>::zero();
+    if (Yin) {
+        const XYZZ<F> *src = Yin + ((size_t)w * S + s) * n_in;
+        for (uint32_t i = first; i < last; i++) acc.add(src[i]);
+    } else if (s < nb) {
+        const XYZZ<F> *src = R + (size_t)w * n_in;
+        for (uint32_t i = first; i < last; i++) if ((i >> s) & 1) acc.add(src[i]);
+    } else if (s == nb) {
+        const XYZZ<F> *src = R + (size_t)w * n_in;
+        for (uint32_t i = first; i < last; i++) acc.add(src[i]);
+    } else if (A) {
+        const XYZZ<F> *src = A + (size_t)w * n_in;
+        for (uint32_t i = first; i < last; i++) acc.add(src[i]);
+    }
+    Yout[((size_t)w * S + s) * n_out + c] = acc;
+}
+// window value = sum A_i + sum R_i + 2^log_len * sum_j 2^j T_j ; written as the (R, A) pair (value, 0) that k_msm_window_combine takes
+template <class F>
+__global__ void k_msm_slice_final(const XYZZ<F> *__restrict__ Y, uint32_t nb, uint32_t log_len, uint32_t W, XYZZ<F> *__restrict__ outR,
+                                  XYZZ<F> *__restrict__ outA) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const XYZZ<F> *y = Y + (size_t)w * (nb + 2);
+    XYZZ<F> acc = XYZZ<F>::zero();
+    for (uint32_t j = nb; j-- > 0;) {
+        acc.dbl();
+        acc.add(y[j]);
+    }
+    for (uint32_t d = 0; d < log_len; d++) acc.dbl();
+    acc.add(y[nb]);
+    acc.add(y[nb + 1]);
+    outR[w] = acc;
+    outA[w] = XYZZ<F>::zero();
+}
+
 // multiexp.rs:223-229: higher = 2^c * higher + this, from the top window down; then the status word.
 template <class F>
 __global__ void k_msm_window_combine(const XYZZ<F> *__restrict__ R, const XYZZ<F> *__restrict__ A, MsmShape sh, Jacobian<F> *__restrict__ out,
@@ -359,9 +410,12 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
     size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
     size_t o_shist = take((cap + 2) * sizeof(uint32_t)), o_scur = take((cap + 2) * sizeof(uint32_t)), o_order = take((nbk + 1) * sizeof(uint32_t));
-    size_t lvl_entries = (size_t)bw * ((sh.B + RED_K - 1) / RED_K);
+    size_t lvl_entries = (size_t)bw * ((sh.B + RED_K - 1) / RED_K) + bw;
     size_t o_r0 = take(lvl_entries * sizeof(XYZZ<F>)), o_a0 = take(lvl_entries * sizeof(XYZZ<F>));
     size_t o_r1 = take(lvl_entries * sizeof(XYZZ<F>)), o_a1 = take(lvl_entries * sizeof(XYZZ<F>));
+    const size_t slice_n = std::min<size_t>(sh.B, SLICE_MAX);
+    const size_t y_entries = (size_t)bw * 18 * ((slice_n + 7) / 8) + 64;  // (nb + 2 <= 17) rows of n/8 sums per window
+    size_t o_y0 = take(y_entries * sizeof(XYZZ<F>)), o_y1 = take((y_entries / 8 + 64 * (size_t)bw * 18) * sizeof(XYZZ<F>));
     int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, off);
     if (rc) return rc;
     char *ws = (char *)ctx->scratch2;
@@ -402,11 +456,11 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
                                                                                   task_cnt, task_off, order, cap, buckets, partials);
     k_msm_combine_split<F><<<2048, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
-    // reduction tree
+    // reduction: 8-ary (R, A) tree while a window has more than SLICE_MAX entries, then the bit-sliced sums
     const XYZZ<F> *inR = buckets, *inA = nullptr;
     uint32_t n_in = sh.B, log_len = 0;
     int pp = 0;
-    do {
+    while (n_in > SLICE_MAX) {
         uint32_t n_out = (n_in + RED_K - 1) / RED_K;
         uint32_t threads = n_out * bw;
         k_msm_reduce_level<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, n_in, lr[pp], la[pp], n_out, bw, log_len);
@@ -415,7 +469,28 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         pp ^= 1;
         n_in = n_out;
         log_len += RED_LOG_K;
-    } while (n_in > 1);
+    }
+    {
+        uint32_t nb = 0;
+        while ((1u << nb) < n_in) nb++;
+        const uint32_t S = nb + 2;
+        XYZZ<F> *ys[2] = {(XYZZ<F> *)(ws + o_y0), (XYZZ<F> *)(ws + o_y1)};
+        const XYZZ<F> *yin = nullptr;
+        int yp = 0;
+        uint32_t cur = n_in;
+        do {
+            uint32_t n_out = (cur + 7) / 8;
+            uint32_t threads = bw * S * n_out;
+            k_msm_slice_sum<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, yin, cur, nb, n_out, bw, ys[yp]);
+            ctx->launches++;
+            yin = ys[yp];
+            yp ^= 1;
+            cur = n_out;
+        } while (cur > 1);
+        k_msm_slice_final<F><<<(bw + 31) / 32, 32, 0, st>>>(yin, nb, log_len, bw, lr[pp], la[pp]);
+        ctx->launches++;
+        inR = lr[pp]; inA = la[pp];
+    }
     MsmShape comb = sh;
     comb.W = bw;
     k_msm_window_combine<F><<<1, 1, 0, st>>>(inR, inA, comb, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
