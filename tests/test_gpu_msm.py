@@ -302,3 +302,25 @@ def test_multiexp_futures_in_flight(worker):
         zk.multiexp_async(worker, (bases, 0), zk.FullDensity(), exps[0])
     for f in pend:
         f.wait()
+
+
+def test_batched_affine_path_matches(worker, monkeypatch):
+    """The opt-in batched-affine accumulation (B200ZK_BA=1, msm_batched_affine.cuh) gives the same group element, including
+    duplicate bases (doubling), opposite points (identity) and oversized buckets."""
+    import zcash_gpu_thesis_b200 as zk
+
+    n = 6000
+    r = util.rng(1600)
+    xy, ks = util.random_bases("g1", r, n)
+    xy[1::7] = xy[0]  # many duplicates: doubling / cancelling pairs inside one bucket
+    exps = util.random_fr_repr(r, n)
+    exps[1::7] = exps[0]
+    exps[r.random(n) < 0.3] = (1, 0, 0, 0)
+    bases = zk.Bases(worker, zk.G1, xy).precompute(0)
+    want = zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)
+    monkeypatch.setenv("B200ZK_BA", "1")
+    got = zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)
+    monkeypatch.delenv("B200ZK_BA")
+    assert np.array_equal(zk.into_affine(worker, zk.G1, got)[0], zk.into_affine(worker, zk.G1, want)[0])
+    st, ref = cref.multiexp("g1", xy, exps)
+    assert st == 0 and np.array_equal(zk.into_affine(worker, zk.G1, got)[0][0], cref.into_affine("g1", ref)[0])

@@ -21,8 +21,11 @@
 #pragma once
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "ec.cuh"
 #include "internal.h"
+#include "msm_batched_affine.cuh"
 
 namespace b200zk {
 
@@ -416,6 +419,13 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     const size_t slice_n = std::min<size_t>(sh.B, SLICE_MAX);
     const size_t y_entries = (size_t)bw * 18 * ((slice_n + 7) / 8) + 64;  // (nb + 2 <= 17) rows of n/8 sums per window
     size_t o_y0 = take(y_entries * sizeof(XYZZ<F>)), o_y1 = take((y_entries / 8 + 64 * (size_t)bw * 18) * sizeof(XYZZ<F>));
+    // batched-affine accumulation (msm_batched_affine.cuh): correct (the whole MSM suite passes with B200ZK_BA=1) but, as
+    // measured on B200 at 2^24 (accumulation 90.5 ms vs 76.7 ms for the XYZZ kernel), slower: its two passes over the
+    // points are bound by dependent gathers, not by the multiplier pipe.  Opt-in only.
+    bool use_ba = false;
+    if (const char *e = getenv("B200ZK_BA")) use_ba = e[0] == '1';
+    const size_t refs_bound = n_exp * sh.W;
+    size_t o_ba = use_ba ? take(ba_workspace_bytes<F>(nbk, refs_bound)) : 0;
     int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, off);
     if (rc) return rc;
     char *ws = (char *)ctx->scratch2;
@@ -444,17 +454,23 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
                                         sorted, status);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->prof_on) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
-    uint32_t *n_split = status + 3;
-    B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, sizeof(uint32_t), st));
-    B200ZK_CUDA(ctx, cudaMemsetAsync(size_hist, 0, (cap + 2) * sizeof(uint32_t), st));
-    k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split, size_hist);
-    ctx->launches += scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
-    ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
-    ctx->launches += 7;  // digits x2, count_tasks, order_buckets, accumulate, combine_split, window_combine
-    k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
-    k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
-                                                                                  task_cnt, task_off, order, cap, buckets, partials);
-    k_msm_combine_split<F><<<2048, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
+    if (use_ba) {
+        auto scan = [&](const uint32_t *in, size_t n, uint32_t *out, uint32_t *tmp) { return scan_u32<uint32_t>(st, in, n, out, nullptr, tmp); };
+        ctx->launches += 3;
+        if ((rc = ba_accumulate<F>(ctx, (const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk, refs_bound, buckets, ws + o_ba, scan))) return rc;
+    } else {
+        uint32_t *n_split = status + 3;
+        B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, sizeof(uint32_t), st));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(size_hist, 0, (cap + 2) * sizeof(uint32_t), st));
+        k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split, size_hist);
+        ctx->launches += scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
+        ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
+        ctx->launches += 7;  // digits x2, count_tasks, order_buckets, accumulate, combine_split, window_combine
+        k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
+        k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
+                                                                                      task_cnt, task_off, order, cap, buckets, partials);
+        k_msm_combine_split<F><<<2048, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
+    }
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
     // reduction: 8-ary (R, A) tree while a window has more than SLICE_MAX entries, then the bit-sliced sums
     const XYZZ<F> *inR = buckets, *inA = nullptr;
