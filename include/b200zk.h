@@ -42,7 +42,8 @@ enum {
     B200ZK_ERR_DEGREE_TOO_LARGE = 3,    /* SynthesisError::PolynomialDegreeTooLarge (domain.rs:59-61) */
     B200ZK_ERR_BAD_ARG = 4,
     B200ZK_ERR_CUDA = 5,
-    B200ZK_ERR_NCCL = 6
+    B200ZK_ERR_NCCL = 6,
+    B200ZK_ERR_DECODE = 7               /* GroupDecodingError (pairing/src/lib.rs:512-530) from the wire-format entry points */
 };
 
 enum { B200ZK_G1 = 1, B200ZK_G2 = 2 };
@@ -97,6 +98,16 @@ int b200zk_bases_from_device(b200zk_ctx *ctx, int group, const void *d_points, s
  * reductions disappear and wider windows pay off.  Costs W x the base memory (12 x 1.5 GiB for 2^24 G1 points at c = 22).
  * window_bits = 0 picks c from n.  Later multiexps on these bases use the table automatically.  Results are unchanged. */
 int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bits);
+/* The wire format of Parameters::read (groth16/mod.rs:287-382): n uncompressed big-endian points (96 B G1 / 192 B G2, Fq2 as
+ * c1 then c0; pairing/src/bls12_381/README.md:59-75).  Decoded on the device straight into Montgomery limbs
+ * (into_affine_unchecked, ec.rs:686-736); checked != 0 adds the curve-equation and subgroup tests of into_affine
+ * (ec.rs:125-144).  Any bad point -> B200ZK_ERR_DECODE with its index and reason in b200zk_last_error(); a point at infinity
+ * is such an error unless allow_infinity (Parameters::read rejects it, mod.rs:300-304). */
+int b200zk_bases_upload_encoded(b200zk_ctx *ctx, int group, const uint8_t *bytes, size_t n, int checked, int allow_infinity, b200zk_bases **out);
+/* Same decode / the matching encode for host arrays (VerifyingKey elements, Proof::write groth16/mod.rs:43-53):
+ * compressed != 0 writes the 48 / 96-byte form with the sign flag (ec.rs:839-868, 2801-2830). */
+int b200zk_decode_points(b200zk_ctx *ctx, int group, const uint8_t *bytes, size_t n, int checked, uint64_t *out_xy, uint8_t *out_inf);
+int b200zk_encode_points(b200zk_ctx *ctx, int group, const uint64_t *xy, const uint8_t *inf, size_t n, int compressed, uint8_t *out_bytes);
 size_t b200zk_bases_len(const b200zk_bases *bases);
 void b200zk_bases_free(b200zk_bases *bases);
 

@@ -14,6 +14,7 @@ from .bellman import (  # noqa: F401
     DeviceBuffer,
     EvaluationDomain,
     FullDensity,
+    GroupDecodingError,
     IoError,
     PolynomialDegreeTooLarge,
     SynthesisError,
@@ -22,6 +23,8 @@ from .bellman import (  # noqa: F401
     Proof,
     Worker,
     create_proof_from_assignment,
+    decode_points,
+    encode_points,
     field_vec,
     fixed_base_mul,
     h_poly,

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200zk.so")
 
-OK, ERR_UNEXPECTED_IDENTITY, ERR_UNEXPECTED_EOF, ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_NCCL = range(7)
+OK, ERR_UNEXPECTED_IDENTITY, ERR_UNEXPECTED_EOF, ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_NCCL, ERR_DECODE = range(8)
 G1, G2 = 1, 2
 FR, FQ = 0, 1
 FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
@@ -38,6 +38,9 @@ SIGNATURES = {
     "b200zk_bases_upload": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, C.POINTER(_vp)]),
     "b200zk_bases_from_device": (_i, [_vp, _i, _vp, _sz, _vp, C.POINTER(_vp)]),
     "b200zk_bases_precompute": (_i, [_vp, _vp, _i]),
+    "b200zk_bases_upload_encoded": (_i, [_vp, _i, _vp, _sz, _i, _i, C.POINTER(_vp)]),
+    "b200zk_decode_points": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp]),
+    "b200zk_encode_points": (_i, [_vp, _i, _vp, _vp, _sz, _i, _vp]),
     "b200zk_bases_len": (_sz, [_vp]),
     "b200zk_bases_free": (None, [_vp]),
     "b200zk_multiexp": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),

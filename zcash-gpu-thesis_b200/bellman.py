@@ -48,6 +48,10 @@ class CudaError(RuntimeError):
     pass
 
 
+class GroupDecodingError(ValueError):
+    """pairing::GroupDecodingError (pairing/src/lib.rs:512-530), raised by the wire-format entry points"""
+
+
 def _raise(worker, st):
     msg = worker.last_error() if worker is not None else ""
     if st == L.ERR_UNEXPECTED_IDENTITY:
@@ -56,6 +60,8 @@ def _raise(worker, st):
         raise IoError(msg or "expected more bases from source")
     if st == L.ERR_DEGREE_TOO_LARGE:
         raise PolynomialDegreeTooLarge(msg)
+    if st == L.ERR_DECODE:
+        raise GroupDecodingError(msg)
     if st == L.ERR_BAD_ARG:
         raise ValueError(msg)
     raise CudaError(f"b200zk status {st}: {msg}")
@@ -243,6 +249,21 @@ class Bases:
         self.worker, self.group, self.n = worker, group, n
         h = C.c_void_p()
         st = worker.lib.b200zk_bases_from_device(worker.ctx, group, dbuf.ptr, n, None if dinf is None else dinf.ptr, C.byref(h))
+        if st:
+            _raise(worker, st)
+        self.handle = h
+        return self
+
+    @classmethod
+    def read(cls, worker, group, data: bytes, checked=False, allow_infinity=False):
+        """The point vectors of Parameters::read (groth16/mod.rs:287-382): uncompressed big-endian points decoded on the device."""
+        pb = 96 if group == L.G1 else 192
+        assert len(data) % pb == 0
+        self = cls.__new__(cls)
+        self.worker, self.group, self.n = worker, group, len(data) // pb
+        buf = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        st = worker.lib.b200zk_bases_upload_encoded(worker.ctx, group, _ptr(buf), self.n, int(checked), int(allow_infinity), C.byref(h))
         if st:
             _raise(worker, st)
         self.handle = h
@@ -452,6 +473,34 @@ def h_poly(worker: Worker, a, b, c):
     return out
 
 
+def decode_points(worker, group, data: bytes, checked=False):
+    """EncodedPoint::into_affine[_unchecked] for uncompressed encodings (ec.rs:686-752): (xy Montgomery limbs, infinity flags)"""
+    pb = 96 if group == L.G1 else 192
+    n = len(data) // pb
+    buf = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros((n, pb // 8), dtype=np.uint64)
+    inf = np.zeros(n, dtype=np.uint8)
+    st = worker.lib.b200zk_decode_points(worker.ctx, group, _ptr(buf), n, int(checked), _ptr(out), _ptr(inf))
+    if st:
+        _raise(worker, st)
+    return out, inf
+
+
+def encode_points(worker, group, xy, inf=None, compressed=False) -> bytes:
+    """into_uncompressed / into_compressed (ec.rs:796-868, 2750-2830) on the device"""
+    w = 12 if group == L.G1 else 24
+    xy = _u64(xy, w)
+    n = xy.shape[0]
+    if inf is not None:
+        inf = np.ascontiguousarray(inf, dtype=np.uint8)
+    size = (w * 8) // (2 if compressed else 1)
+    out = np.zeros(n * size, dtype=np.uint8)
+    st = worker.lib.b200zk_encode_points(worker.ctx, group, _ptr(xy), _ptr(inf), n, int(compressed), _ptr(out))
+    if st:
+        _raise(worker, st)
+    return out.tobytes()
+
+
 # ------------------------------------------------------------------------------------------------------ test / bench helpers
 def field_vec(worker, field, op, a, b=None):
     w = 4 if field == L.FR else 6
@@ -549,28 +598,11 @@ class Proof:
         self.a, self.b, self.c, self.inf = a, b, c, [bool(x) for x in inf]
 
     def write(self, worker) -> bytes:
-        """Proof::write: 48 + 96 + 48 compressed big-endian bytes (ec.rs:839-868, 2801-2830)."""
-        coords = np.concatenate([self.a, self.b, self.c]).reshape(-1, 6)
-        canon = field_vec(worker, L.FQ, L.OP_INTO_REPR, coords)  # Montgomery -> canonical on the device
-        ints = [sum(int(v) << (64 * i) for i, v in enumerate(row)) for row in canon]
-        ax, ay, bx0, bx1, by0, by1, cx, cy = ints
-
-        def g1(x, y, inf):
-            if inf:
-                return bytes([0xC0]) + bytes(47)
-            out = bytearray(x.to_bytes(48, "big"))
-            out[0] |= 0x80 | (0x20 if y > (FQ_MODULUS - y) % FQ_MODULUS else 0)
-            return bytes(out)
-
-        def g2(x0, x1, y0, y1, inf):
-            if inf:
-                return bytes([0xC0]) + bytes(95)
-            out = bytearray(x1.to_bytes(48, "big") + x0.to_bytes(48, "big"))  # c1 then c0
-            ny0, ny1 = (FQ_MODULUS - y0) % FQ_MODULUS, (FQ_MODULUS - y1) % FQ_MODULUS
-            out[0] |= 0x80 | (0x20 if (y1, y0) > (ny1, ny0) else 0)
-            return bytes(out)
-
-        return g1(ax, ay, self.inf[0]) + g2(bx0, bx1, by0, by1, self.inf[1]) + g1(cx, cy, self.inf[2])
+        """Proof::write: 48 + 96 + 48 compressed big-endian bytes (groth16/mod.rs:43-53; ec.rs:839-868, 2801-2830), encoded on the device."""
+        a = encode_points(worker, L.G1, self.a, [self.inf[0]], compressed=True)
+        b = encode_points(worker, L.G2, self.b, [self.inf[1]], compressed=True)
+        c = encode_points(worker, L.G1, self.c, [self.inf[2]], compressed=True)
+        return a + b + c
 
 
 def create_proof_from_assignment(worker, params: Parameters, a, b, c, input_assignment, aux_assignment, a_aux_density, b_input_density,

@@ -255,6 +255,87 @@ int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bit
     return msm_precompute(ctx, bases, c);
 }
 
+static int decode_error(b200zk_ctx *ctx, unsigned long long e) {
+    static const char *why[] = {"ok", "unexpected compression mode", "unexpected information in the flag bits", "coordinate is not in the field",
+                                "point is not on the curve", "point is not in the prime-order subgroup", "point at infinity"};
+    unsigned code = (unsigned)(e & 0xff);
+    return set_error(ctx, B200ZK_ERR_DECODE, "point " + std::to_string(e >> 8) + ": " + (code < 7 ? why[code] : "decoding error"));
+}
+
+// bytes (host) -> packed affine + infinity flags in freshly allocated device buffers
+static int decode_to_device(b200zk_ctx *ctx, int group, const uint8_t *bytes, size_t n, int checked, int allow_infinity, void **d_pts, uint8_t **d_inf) {
+    const size_t pb = point_bytes(group);
+    *d_pts = nullptr;
+    *d_inf = nullptr;
+    void *d_bytes = nullptr;
+    unsigned long long *d_err = nullptr;
+    B200ZK_CUDA(ctx, cudaMalloc(d_pts, n ? n * pb : 1));
+    B200ZK_CUDA(ctx, cudaMalloc((void **)d_inf, n ? n : 1));
+    B200ZK_CUDA(ctx, cudaMalloc(&d_bytes, n ? n * pb : 1));
+    B200ZK_CUDA(ctx, cudaMalloc((void **)&d_err, 8));
+    B200ZK_CUDA(ctx, cudaMemsetAsync(d_err, 0xff, 8, ctx->stream));
+    if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(d_bytes, bytes, n * pb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = codec_decode_uncompressed(ctx, group, d_bytes, n, checked, allow_infinity, *d_pts, *d_inf, d_err);
+    unsigned long long e = ~0ull;
+    if (!rc && cudaMemcpyAsync(&e, d_err, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = B200ZK_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_error(ctx, B200ZK_ERR_CUDA, "decode failed");
+    cudaFree(d_bytes);
+    cudaFree(d_err);
+    if (!rc && e != ~0ull) rc = decode_error(ctx, e);
+    if (rc) { cudaFree(*d_pts); cudaFree(*d_inf); *d_pts = nullptr; *d_inf = nullptr; }
+    return rc;
+}
+
+int b200zk_bases_upload_encoded(b200zk_ctx *ctx, int group, const uint8_t *bytes, size_t n, int checked, int allow_infinity, b200zk_bases **out) {
+    CHECK_CTX(ctx);
+    if (!out || (n && !bytes) || (group != B200ZK_G1 && group != B200ZK_G2)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad argument");
+    USE_DEVICE(ctx);
+    void *d_pts;
+    uint8_t *d_inf;
+    int rc = decode_to_device(ctx, group, bytes, n, checked, allow_infinity, &d_pts, &d_inf);
+    if (rc) return rc;
+    b200zk_bases *b = new b200zk_bases();
+    b->ctx = ctx; b->group = group; b->n = n; b->points = d_pts; b->infinity = nullptr;
+    if (allow_infinity) b->infinity = d_inf; else cudaFree(d_inf);  // without allow_infinity no base is the identity
+    *out = b;
+    return B200ZK_OK;
+}
+
+int b200zk_decode_points(b200zk_ctx *ctx, int group, const uint8_t *bytes, size_t n, int checked, uint64_t *out_xy, uint8_t *out_inf) {
+    CHECK_CTX(ctx);
+    if ((n && (!bytes || !out_xy)) || (group != B200ZK_G1 && group != B200ZK_G2)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad argument");
+    USE_DEVICE(ctx);
+    void *d_pts;
+    uint8_t *d_inf;
+    int rc = decode_to_device(ctx, group, bytes, n, checked, 1, &d_pts, &d_inf);
+    if (rc) return rc;
+    cudaError_t e1 = n ? cudaMemcpy(out_xy, d_pts, n * point_bytes(group), cudaMemcpyDeviceToHost) : cudaSuccess;
+    cudaError_t e2 = (n && out_inf) ? cudaMemcpy(out_inf, d_inf, n, cudaMemcpyDeviceToHost) : cudaSuccess;
+    cudaFree(d_pts);
+    cudaFree(d_inf);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error(ctx, B200ZK_ERR_CUDA, "copy back failed");
+    return B200ZK_OK;
+}
+
+int b200zk_encode_points(b200zk_ctx *ctx, int group, const uint64_t *xy, const uint8_t *inf, size_t n, int compressed, uint8_t *out_bytes) {
+    CHECK_CTX(ctx);
+    if ((n && (!xy || !out_bytes)) || (group != B200ZK_G1 && group != B200ZK_G2)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad argument");
+    USE_DEVICE(ctx);
+    if (n == 0) return B200ZK_OK;
+    const size_t pb = point_bytes(group), ob = compressed ? pb / 2 : pb;
+    size_t o_inf = (n * pb + 255) / 256 * 256, o_out = o_inf + (n + 255) / 256 * 256;
+    int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, o_out + n * ob + 256);
+    if (rc) return rc;
+    char *s = (char *)ctx->scratch;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s, xy, n * pb, cudaMemcpyHostToDevice, ctx->stream));
+    if (inf) B200ZK_CUDA(ctx, cudaMemcpyAsync(s + o_inf, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = codec_encode(ctx, group, s, inf ? (const uint8_t *)(s + o_inf) : nullptr, n, compressed, s + o_out);
+    if (rc) return rc;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out_bytes, s + o_out, n * ob, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
 size_t b200zk_bases_len(const b200zk_bases *bases) { return bases ? bases->n : 0; }
 
 void b200zk_bases_free(b200zk_bases *bases) {

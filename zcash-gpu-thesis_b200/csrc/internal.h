@@ -101,6 +101,10 @@ int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_ou
 int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out);
 int msm_precompute(Ctx *ctx, Bases *bases, uint32_t c);
 int msm_build_table(Ctx *ctx, int group, const void *d_base_affine, void *d_table, uint32_t nwin);  // 255 * nwin XYZZ entries
+// codec.cu
+int codec_decode_uncompressed(Ctx *ctx, int group, const void *d_bytes, size_t n, int checked, int allow_infinity, void *d_out, uint8_t *d_inf,
+                              unsigned long long *d_err);
+int codec_encode(Ctx *ctx, int group, const void *d_pts, const uint8_t *d_inf, size_t n, int compressed, void *d_out);
 // groth16.cu
 struct Crs {
     Ctx *ctx;
