@@ -16,7 +16,7 @@
 namespace b200zk {
 
 static constexpr uint32_t LO_BITS = 12;  // two-level g^i table: g^i = lo[i & 4095] * hi[i >> 12]
-static constexpr int NTT_THREADS = 256;
+static constexpr int NTT_THREADS = 128;
 static constexpr uint32_t MAX_TILE_LOG = 10;
 
 enum { C_OMEGA = 0, C_OMEGA_INV = 1, C_N_INV = 2, C_G = 3, C_G_INV = 4, C_Z_INV = 5, C_G_STEP = 6, C_GI_STEP = 7, C_COUNT = 8 };
@@ -78,7 +78,7 @@ __device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t tile, uint32_t e
     for (int l = 0; l < 8; l++) sm[l * tile + e] = x.v[l];
 }
 
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_ntt_pass(const fr_t *__restrict__ in, fr_t *__restrict__ out, const fr_t *__restrict__ tw,
+__global__ void __launch_bounds__(NTT_THREADS, 7) k_ntt_pass(const fr_t *__restrict__ in, fr_t *__restrict__ out, const fr_t *__restrict__ tw,
                                                          const fr_t *__restrict__ sc_lo, const fr_t *__restrict__ sc_hi,
                                                          const fr_t *__restrict__ consts, NttPass p) {
     extern __shared__ uint32_t sm[];
