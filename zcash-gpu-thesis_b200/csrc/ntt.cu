@@ -227,6 +227,7 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         p.s0 = s0;
         p.B = base + (ps < extra ? 1 : 0);
         p.q = npass == 1 ? 0 : (MAX_TILE_LOG - p.B < 2 ? MAX_TILE_LOG - p.B : 2);
+        while (p.q > 0 && (n >> (p.B + p.q)) < (size_t)2 * ctx->sm_count) p.q--;  // small transforms: more, narrower tiles to fill the SMs
         p.bitrev_load = ps == 0;
         p.pre_scale = (ps == 0 && kind == B200ZK_COSET_FFT) ? 1 : 0;
         p.post_scale = ps + 1 == npass ? (kind == B200ZK_IFFT ? 1 : kind == B200ZK_ICOSET_FFT ? 2 : 0) : 0;
