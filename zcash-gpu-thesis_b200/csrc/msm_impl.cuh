@@ -199,18 +199,21 @@ template <class F>
 __global__ void __launch_bounds__(128, sizeof(F) > 48 ? 2 : B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                        const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
                                                        const uint32_t *__restrict__ task_off, const uint32_t *__restrict__ order, uint32_t cap,
-                                                       XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ partials) {
+                                                       uint32_t max_tasks, XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t beg, end;
     XYZZ<F> *dst;
-    if (t < n_buckets) {
+    // the split tasks (the longest chains) come first in the grid so they start in the first wave
+    if (t >= max_tasks) {
+        t -= max_tasks;
+        if (t >= n_buckets) return;
         uint32_t b = order[t];
         if (task_cnt[b]) return;  // handled by its split tasks
         beg = offsets[b];
         end = offsets[b + 1];
         dst = buckets + b;
     } else {
-        uint32_t task = t - n_buckets;
+        uint32_t task = t;
         if (task >= task_off[n_buckets]) return;
         // bucket b with task_off[b] <= task < task_off[b + 1]
         uint32_t lo = 0, hi = n_buckets;
@@ -408,7 +411,8 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_sorted = take(n_exp * sh.W * sizeof(uint32_t));
     size_t o_buckets = take(nbk * sizeof(XYZZ<F>));
     // bucket splitting: cap = 2 x mean bucket load + 32; at most n*W/cap + nbk... split tasks, bounded by 2*n*W/cap
-    const uint32_t cap = (uint32_t)(2 * (n_exp * (sh.W / bw) / sh.B) + 32);
+    const size_t mean_load = n_exp * (sh.W / bw) / sh.B;
+    const uint32_t cap = (uint32_t)(mean_load + mean_load / 2 + 32);  // chains longer than ~1.5 x the mean are split
     const size_t max_tasks = (size_t)2 * n_exp * sh.W / cap + 2;
     size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
     size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
@@ -468,7 +472,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         ctx->launches += 7;  // digits x2, count_tasks, order_buckets, accumulate, combine_split, window_combine
         k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
         k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
-                                                                                      task_cnt, task_off, order, cap, buckets, partials);
+                                                                                      task_cnt, task_off, order, cap, (uint32_t)max_tasks, buckets, partials);
         k_msm_combine_split<F><<<2048, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
     }
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
