@@ -242,7 +242,98 @@ struct __align__(16) Fp {
         final_sub(r.v);
         return r;
     }
-    __device__ __forceinline__ Fp sqr() const { return *this * *this; }  // fq.rs:965-1002
+    // fq.rs:965-1002 square: the off-diagonal products a_i a_j (i < j) are formed once and doubled, 78 instead of 144
+    // multiplier instructions for the product; then the same Montgomery rows as the product, without the a*b part.
+    __device__ __forceinline__ Fp sqr() const {
+#ifdef B200ZK_INLINE_MUL
+        return sqr_inline(*this);
+#else
+        return sqr_call(*this);
+#endif
+    }
+    static __device__ __noinline__ Fp sqr_call(Fp a) { return sqr_inline(a); }
+    __device__ __forceinline__ static Fp sqr_inline(const Fp &a) {
+        // E: products whose position i + j is even (64-bit aligned at even limbs); O: odd positions, O[k] sits at limb k + 1
+        uint32_t E[2 * N], O[2 * N];
+#pragma unroll
+        for (int k = 0; k < 2 * N; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) {
+            if (i + 2 < N) {
+#pragma unroll
+                for (int j = i + 2; j < N; j += 2) {
+                    E[i + j] = j == i + 2 ? mad_lo_cc(a.v[i], a.v[j], E[i + j]) : madc_lo_cc(a.v[i], a.v[j], E[i + j]);
+                    E[i + j + 1] = madc_hi_cc(a.v[i], a.v[j], E[i + j + 1]);
+                }
+                constexpr int dummy = 0; (void)dummy;
+                const int last = i + (i + 2 + ((N - 1 - (i + 2)) / 2) * 2) + 1;  // limb of the last high half
+#pragma unroll
+                for (int k = last + 1; k < 2 * N - 1; k++) E[k] = addc_cc(E[k], 0);
+                if (last + 1 <= 2 * N - 1) E[2 * N - 1] = addc(E[2 * N - 1], 0);
+            }
+            {
+#pragma unroll
+                for (int j = i + 1; j < N; j += 2) {
+                    O[i + j - 1] = j == i + 1 ? mad_lo_cc(a.v[i], a.v[j], O[i + j - 1]) : madc_lo_cc(a.v[i], a.v[j], O[i + j - 1]);
+                    O[i + j] = madc_hi_cc(a.v[i], a.v[j], O[i + j]);
+                }
+                const int last = i + (i + 1 + ((N - 1 - (i + 1)) / 2) * 2);
+#pragma unroll
+                for (int k = last + 1; k < 2 * N - 1; k++) O[k] = addc_cc(O[k], 0);
+                if (last + 1 <= 2 * N - 1) O[2 * N - 1] = addc(O[2 * N - 1], 0);
+            }
+        }
+        // U = E + (O << 32), T = 2 U + sum a_i^2 2^(64 i)
+        uint32_t T[2 * N];
+        T[0] = E[0];
+        T[1] = add_cc(E[1], O[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) T[k] = addc_cc(E[k], O[k - 1]);
+        T[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
+#pragma unroll
+        for (int k = 2 * N - 1; k > 0; k--) T[k] = __funnelshift_l(T[k - 1], T[k], 1);
+        T[0] <<= 1;
+        T[0] = mad_lo_cc(a.v[0], a.v[0], T[0]);
+        T[1] = madc_hi_cc(a.v[0], a.v[0], T[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) { T[2 * i] = madc_lo_cc(a.v[i], a.v[i], T[2 * i]); T[2 * i + 1] = madc_hi_cc(a.v[i], a.v[i], T[2 * i + 1]); }
+        T[2 * N - 2] = madc_lo_cc(a.v[N - 1], a.v[N - 1], T[2 * N - 2]);
+        T[2 * N - 1] = madc_hi(a.v[N - 1], a.v[N - 1], T[2 * N - 1]);
+        // Montgomery reduction of the low half (the rows of mad_n_redc without the a*b part), then + high half
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) { even[k] = T[k]; odd[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            redc_row(even, odd, i == 0);
+            redc_row(odd, even, false);
+        }
+        Fp r;
+        r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(even[i], odd[i + 1]);
+        r.v[N - 1] = addc(even[N - 1], 0);
+        r.v[0] = add_cc(r.v[0], T[N]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(r.v[i], T[N + i]);
+        r.v[N - 1] = addc(r.v[N - 1], T[2 * N - 1]);
+        final_sub(r.v);
+        return r;
+    }
+    // one reduction row: T += m p; T >>= 32 (roles of even / odd swap at the caller)
+    __device__ __forceinline__ static void redc_row(uint32_t *even, uint32_t *odd, bool first) {
+        if (!first) {
+            even[0] = add_cc(even[0], odd[1]);  // stray limb; the carry is absorbed while odd shifts down by two limbs
+#pragma unroll
+            for (int j = 0; j < N - 2; j++) odd[j] = addc_cc(odd[j + 2], 0);
+            odd[N - 2] = addc(0, 0);
+            odd[N - 1] = 0;
+        }
+        uint32_t mi = even[0] * B200ZK_M0_RT[P::N == 8 ? 0 : 1];
+        cmad_mod<1>(odd, mi);
+        cmad_mod<0>(even, mi);
+        odd[N - 1] = addc(odd[N - 1], 0);
+    }
 
     // Montgomery -> canonical (fr.rs:290-303 into_repr) and back (fr.rs:279-288 from_repr)
     __device__ __forceinline__ Fp from_mont() const { Fp o = zero(); o.v[0] = 1; return *this * o; }
