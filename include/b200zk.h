@@ -133,6 +133,10 @@ int b200zk_multiexp_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_
 typedef struct b200zk_job b200zk_job;
 int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
                           const uint8_t *density, b200zk_job **job);
+/* Multi-GPU form: this rank's (bases, scalars) are its shard; the job's result is the sum over all ranks of the communicator
+ * (NCCL all-gather of the partials + adds, enqueued right behind the shard's multiexp). Every rank must submit the call. */
+int b200zk_multiexp_sharded_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                                  const uint8_t *density, b200zk_job **job);
 int b200zk_job_wait(b200zk_job *job, uint64_t *out_jacobian);
 /* Pippenger window override for tuning (0 = automatic). */
 int b200zk_set_msm_window(b200zk_ctx *ctx, int window_bits);

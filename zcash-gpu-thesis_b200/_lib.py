@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200zk_multiexp": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "b200zk_multiexp_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "b200zk_multiexp_async": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, C.POINTER(_vp)]),
+    "b200zk_multiexp_sharded_async": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, C.POINTER(_vp)]),
     "b200zk_job_wait": (_i, [_vp, _vp]),
     "b200zk_set_msm_window": (_i, [_vp, _i]),
     "b200zk_sum_points_dev": (_i, [_vp, _i, _vp, _sz, _vp]),

@@ -390,8 +390,10 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
     return B200ZK_OK;
 }
 
-int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
-                          const uint8_t *density, b200zk_job **job) {
+static int allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total);
+
+static int multiexp_async_impl(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                               const uint8_t *density, b200zk_job **job, bool gather) {
     CHECK_CTX(ctx);
     if (!bases || !job || (n_exp && !scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
     USE_DEVICE(ctx);
@@ -420,6 +422,9 @@ int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t bas
     int rc = msm_run(ctx, bases, base_offset, d, n_exp, density ? (const uint8_t *)(d + o_den) : nullptr, d + o_res, d + o_st, ctx->window_override);
     if (rc) return rc;
     const size_t jac_bytes = bases->group == B200ZK_G1 ? 144 : 288;
+    if (gather && ctx->world > 1) {  // this rank's shard partial -> sum over all ranks (NCCL all-gather + adds on the same stream)
+        if ((rc = allgather_sum_dev(ctx, bases->group, d + o_res, d + o_res))) return rc;
+    }
     B200ZK_CUDA(ctx, cudaMemcpyAsync(sl.host_res, d + o_res, jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaMemcpyAsync((char *)sl.host_res + 320, d + o_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
@@ -427,6 +432,15 @@ int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t bas
     b200zk_job *j = new b200zk_job{ctx, si, bases->group, o_res, o_st};
     *job = j;
     return B200ZK_OK;
+}
+
+int b200zk_multiexp_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                          const uint8_t *density, b200zk_job **job) {
+    return multiexp_async_impl(ctx, bases, base_offset, scalars, n_exp, density, job, false);
+}
+int b200zk_multiexp_sharded_async(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                                  const uint8_t *density, b200zk_job **job) {
+    return multiexp_async_impl(ctx, bases, base_offset, scalars, n_exp, density, job, true);
 }
 
 int b200zk_job_wait(b200zk_job *job, uint64_t *out_jacobian) {
@@ -509,10 +523,13 @@ int b200zk_comm_init(b200zk_ctx *ctx, const uint8_t unique_id[128], int rank, in
 int b200zk_allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total) {
     CHECK_CTX(ctx);
     USE_DEVICE(ctx);
+    return allgather_sum_dev(ctx, group, d_partial, d_total);
+}
+static int allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total) {
     const size_t jb = group == B200ZK_G1 ? 144 : 288;
     if (ctx->world == 1 || !ctx->nccl_comm) {
         if (ctx->world != 1) return set_error(ctx, B200ZK_ERR_NCCL, "communicator not initialised");
-        B200ZK_CUDA(ctx, cudaMemcpyAsync(d_total, d_partial, jb, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (d_total != d_partial) B200ZK_CUDA(ctx, cudaMemcpyAsync(d_total, d_partial, jb, cudaMemcpyDeviceToDevice, ctx->stream));
         return B200ZK_OK;
     }
     int r = g_nccl.AllGather(d_partial, ctx->gather_buf, jb, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream);
