@@ -54,6 +54,12 @@ struct FrParams {
 };
 struct FqParams {
     static constexpr int N = 12;
+    __device__ __host__ static constexpr uint32_t mod_sq(int i) {  // q^2, 24 limbs (keeps the lazy Fq2 differences positive)
+        constexpr uint32_t m[24] = {0x1c718e39u, 0x26aa0000u, 0x76382eabu, 0x7ced6b1du, 0x62113cfdu, 0x162c3383u, 0x3e71b743u, 0x66bf91edu,
+                                    0x7091a049u, 0x292e85a8u, 0x86185c7bu, 0x1d68619cu, 0x0978ef01u, 0xf5314933u, 0x16ddca6eu, 0x50a62cfdu,
+                                    0x349e8bd0u, 0x66e59e49u, 0x0e7046b4u, 0xe2dc90e5u, 0xa22f25e9u, 0x4bd278eau, 0xb8c35fc7u, 0x02a437a4u};
+        return m[i];
+    }
     static constexpr uint32_t M0 = 0xfffcfffdu;  // low word of INV = 0x89f3fffcfffcfffd
     __device__ __host__ static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
@@ -299,7 +305,11 @@ struct __align__(16) Fp {
         for (int i = 1; i < N - 1; i++) { T[2 * i] = madc_lo_cc(a.v[i], a.v[i], T[2 * i]); T[2 * i + 1] = madc_hi_cc(a.v[i], a.v[i], T[2 * i + 1]); }
         T[2 * N - 2] = madc_lo_cc(a.v[N - 1], a.v[N - 1], T[2 * N - 2]);
         T[2 * N - 1] = madc_hi(a.v[N - 1], a.v[N - 1], T[2 * N - 1]);
-        // Montgomery reduction of the low half (the rows of mad_n_redc without the a*b part), then + high half
+        return redc_wide(T);
+    }
+    // Montgomery reduction of an unreduced 2N-limb value T < 2 p^2: the rows of mad_n_redc without the a*b part on the low
+    // half, then + high half; one conditional subtraction gives the canonical result
+    __device__ __forceinline__ static Fp redc_wide(const uint32_t *T) {
         uint32_t even[N], odd[N];
 #pragma unroll
         for (int k = 0; k < N; k++) { even[k] = T[k]; odd[k] = 0; }
@@ -319,6 +329,44 @@ struct __align__(16) Fp {
         r.v[N - 1] = addc(r.v[N - 1], T[2 * N - 1]);
         final_sub(r.v);
         return r;
+    }
+    // T = a * b, 2N limbs, not reduced (operands may be < 2p: used by the lazy-reduction Fq2 product)
+    __device__ __forceinline__ static void mul_wide(uint32_t *T, const uint32_t *a, const uint32_t *b) {
+        uint32_t E[2 * N], O[2 * N];  // E: even positions i + j; O[k] sits at limb k + 1 (odd positions)
+#pragma unroll
+        for (int k = 0; k < 2 * N; k++) { E[k] = 0; O[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            {   // j = i mod 2, +2, ...: even positions
+                const int j0 = i & 1;
+#pragma unroll
+                for (int j = j0; j < N; j += 2) {
+                    E[i + j] = j == j0 ? mad_lo_cc(a[j], b[i], E[i + j]) : madc_lo_cc(a[j], b[i], E[i + j]);
+                    E[i + j + 1] = madc_hi_cc(a[j], b[i], E[i + j + 1]);
+                }
+                const int last = i + (j0 + ((N - 1 - j0) / 2) * 2) + 1;
+#pragma unroll
+                for (int k = last + 1; k < 2 * N - 1; k++) E[k] = addc_cc(E[k], 0);
+                if (last + 1 <= 2 * N - 1) E[2 * N - 1] = addc(E[2 * N - 1], 0);
+            }
+            {   // odd positions
+                const int j0 = (i + 1) & 1;
+#pragma unroll
+                for (int j = j0; j < N; j += 2) {
+                    O[i + j - 1] = j == j0 ? mad_lo_cc(a[j], b[i], O[i + j - 1]) : madc_lo_cc(a[j], b[i], O[i + j - 1]);
+                    O[i + j] = madc_hi_cc(a[j], b[i], O[i + j]);
+                }
+                const int last = i + (j0 + ((N - 1 - j0) / 2) * 2);
+#pragma unroll
+                for (int k = last + 1; k < 2 * N - 1; k++) O[k] = addc_cc(O[k], 0);
+                if (last + 1 <= 2 * N - 1) O[2 * N - 1] = addc(O[2 * N - 1], 0);
+            }
+        }
+        T[0] = E[0];
+        T[1] = add_cc(E[1], O[0]);
+#pragma unroll
+        for (int k = 2; k < 2 * N - 1; k++) T[k] = addc_cc(E[k], O[k - 1]);
+        T[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
     }
     // one reduction row: T += m p; T >>= 32 (roles of even / odd swap at the caller)
     __device__ __forceinline__ static void redc_row(uint32_t *even, uint32_t *odd, bool first) {
