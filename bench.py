@@ -511,10 +511,12 @@ def bench_spend_proofs(w, zk, rng, world):
         d[rng.choice(n, size=total, replace=False)] = 1
         return d
 
-    ev = [random_scalars(rng, n_con) for _ in range(3)]
+    # the assignment a prover hands over lives in page-locked memory (the e2e rule: H2D from pinned host memory)
+    ev = [w.pinned_copy(random_scalars(rng, n_con)) for _ in range(3)]
     inputs, aux = witness(n_in), witness(n_aux)
     inputs[0] = (1, 0, 0, 0)
-    da, dbi, dba = density(n_aux, a_dense), density(n_in, b_in_dense), density(n_aux, b_aux_dense)
+    inputs, aux = w.pinned_copy(inputs), w.pinned_copy(aux)
+    da, dbi, dba = (w.pinned_copy(x) for x in (density(n_aux, a_dense), density(n_in, b_in_dense), density(n_aux, b_aux_dense)))
     r, s = 0x1234567890ABCDEF1234567890ABCDEF, 0x0FEDCBA0987654321FEDCBA098765432
 
     def prove(worker):
@@ -532,7 +534,7 @@ def bench_spend_proofs(w, zk, rng, world):
     workers = [zk.Worker(w.device) for _ in range(streams)]
     for x in workers:
         prove(x)
-    per_thread = 6
+    per_thread = env_int("B200ZK_SPEND_PER_STREAM", 6)
 
     def loop(x):
         for _ in range(per_thread):

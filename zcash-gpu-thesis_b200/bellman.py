@@ -139,6 +139,7 @@ class Worker:
             raise CudaError(f"b200zk_init(device={device}) failed with status {st}: no usable CUDA device (there is no CPU fallback)")
         self.ctx = ctx
         self.device = device
+        self._pinned = []
 
     def last_error(self):
         return (self.lib.b200zk_last_error(self.ctx) or b"").decode()
@@ -182,8 +183,30 @@ class Worker:
             _raise(self, st)
         return out.value
 
+    def pinned_array(self, shape, dtype=np.uint64):
+        """A numpy array over page-locked host memory (b200zk_host_alloc_pinned): copies from it are true DMA transfers that
+        overlap kernels, where a pageable Vec is staged through the driver.  Freed with the worker (or `free_pinned`)."""
+        dt = np.dtype(dtype)
+        count = int(np.prod(shape))
+        hp = C.c_void_p()
+        st = self.lib.b200zk_host_alloc_pinned(max(1, count * dt.itemsize), C.byref(hp))
+        if st:
+            _raise(self, st)
+        self._pinned.append(hp)
+        buf = (C.c_uint8 * (count * dt.itemsize)).from_address(hp.value)
+        return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+    def pinned_copy(self, arr):
+        arr = np.ascontiguousarray(arr)
+        out = self.pinned_array(arr.shape, arr.dtype)
+        out[...] = arr
+        return out
+
     def close(self):
         if self.ctx is not None:
+            for hp in self._pinned:
+                self.lib.b200zk_host_free_pinned(hp)
+            self._pinned = []
             self.lib.b200zk_destroy(self.ctx)
             self.ctx = None
 

@@ -74,6 +74,18 @@ struct b200zk_bases : public Bases {};
 struct b200zk_crs : public Crs {};
 struct b200zk_job { b200zk_ctx *ctx; int slot; int group; size_t o_res, o_st; };
 
+namespace b200zk {
+int ctx_lanes(Ctx *ctx, int n) {
+    while ((int)ctx->lanes.size() < n) {
+        b200zk_ctx *lane = nullptr;
+        int rc = b200zk_init(ctx->device, &lane);
+        if (rc) return set_error(ctx, rc, "could not create a prover lane");
+        ctx->lanes.push_back(lane);
+    }
+    return B200ZK_OK;
+}
+}  // namespace b200zk
+
 #define CHECK_CTX(ctx) do { if (!(ctx)) return B200ZK_ERR_BAD_ARG; } while (0)
 #define USE_DEVICE(ctx) B200ZK_CUDA(ctx, cudaSetDevice((ctx)->device))
 
@@ -99,6 +111,8 @@ int b200zk_init(int device, b200zk_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200ZK_ERR_CUDA; }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = ctx;
     return B200ZK_OK;
@@ -108,6 +122,11 @@ void b200zk_destroy(b200zk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (Ctx *lane : ctx->lanes) b200zk_destroy(static_cast<b200zk_ctx *>(lane));
+    ctx->lanes.clear();
+    cudaSetDevice(ctx->device);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     ntt_free_all_tables(ctx);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     cudaFree(ctx->gather_buf);
@@ -249,6 +268,7 @@ int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bit
         // small n: c = log2 n keeps ~50 points per bucket and tens of thousands of buckets (threads) in flight;
         // large n: the single bucket set must stay a few percent of the adds
         c = lg < 19 ? lg : lg - 1;
+        if (const char *e = getenv("B200ZK_PRE_DELTA")) c = lg - (uint32_t)atoi(e);
         if (c < 8) c = 8;
         if (c > 22) c = 22;
     }

@@ -10,6 +10,9 @@
 //        [ = rs*delta_g1 + s*alpha_g1 + r*beta_g1 + s*a_answer + r*b1_answer + h + l ]
 // r*delta_g1 and s*delta_g2 use per-CRS window tables (32 windows x 255 multiples, built once at upload, summed by a
 // warp tree); the two variable-base products are MSB-first double-and-add with the reference's Jacobian formulas.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ec.cuh"
 #include "internal.h"
 
@@ -41,45 +44,8 @@ __device__ void table_mul_warp(const XYZZ<F> *table, const uint32_t *scalar, XYZ
     out = sm[0];
 }
 
-__global__ void __launch_bounds__(32) k_proof_stage1(const g1_xyzz_t *table_d1, const g2_xyzz_t *table_d2, const uint32_t *scal,
-                                                    const g1_affine_t *vk_g1 /* alpha, beta, delta */, const g2_affine_t *vk_g2 /* beta, delta */,
-                                                    const g1_jac_t *res_g1, const g2_jac_t *res_g2, g1_jac_t *out_g1 /* g_a, B1 */,
-                                                    g2_affine_t *proof_b, uint8_t *inf_flags) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (blockIdx.x == 0) {
-        g1_xyzz_t *sm = reinterpret_cast<g1_xyzz_t *>(smem_raw);
-        g1_xyzz_t t;
-        table_mul_warp<fq_t>(table_d1, scal, sm, t);
-        if (threadIdx.x == 0) {
-            t.add_mixed(vk_g1[0], false);
-            t.add(g1_xyzz_t::from_jacobian(res_g1[R_A]));
-            out_g1[0] = t.to_jacobian();
-            g1_xyzz_t b1 = g1_xyzz_t::from_affine(vk_g1[1]);
-            b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1]));
-            out_g1[1] = b1.to_jacobian();
-        }
-    } else {
-        g2_xyzz_t *sm = reinterpret_cast<g2_xyzz_t *>(smem_raw);
-        g2_xyzz_t t;
-        table_mul_warp<fq2_t>(table_d2, scal + 8, sm, t);
-        if (threadIdx.x == 0) {
-            t.add_mixed(vk_g2[0], false);
-            t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2]));
-            g2_affine_t a;
-            bool ok = jacobian_to_affine(t.to_jacobian(), a);
-            *proof_b = a;
-            inf_flags[1] = ok ? 0 : 1;
-        }
-    }
-}
-
-// out[b] = scal_sel[b] * in[b]  (CurveProjective::mul_assign, ec.rs:528-552: MSB-first double and add), b = blockIdx.x in {0, 1}:
-// block 0: s * g_a, block 1: r * B1
-__global__ void k_proof_stage2(const g1_jac_t *in, const uint32_t *scal, g1_jac_t *out) {
-    if (threadIdx.x != 0) return;
-    const uint32_t b = blockIdx.x;
-    const uint32_t *k = scal + (b == 0 ? 8 : 0);
-    g1_jac_t p = in[b];
+// CurveProjective::mul_assign (ec.rs:528-552): MSB-first double and add over the 256 bits of a canonical FrRepr
+__device__ g1_jac_t jacobian_mul(const g1_jac_t &p, const uint32_t *k) {
     g1_jac_t acc = g1_jac_t::zero();
     bool found = false;
     for (int i = 255; i >= 0; i--) {
@@ -87,28 +53,63 @@ __global__ void k_proof_stage2(const g1_jac_t *in, const uint32_t *scal, g1_jac_
         if (found) jacobian_double(acc); else found = bit;
         if (bit) jacobian_add(acc, p);
     }
-    out[b] = acc;
+    return acc;
 }
 
-// block 0: proof.a = affine(g_a); block 1: proof.c = affine(s*g_a + r*B1 + h + l)
-__global__ void k_proof_stage3(const g1_jac_t *ga_b1, const g1_jac_t *prods, const g1_jac_t *res_g1, g1_affine_t *proof_a, g1_affine_t *proof_c,
-                               uint8_t *inf_flags) {
+// The assembly is cut along the multiexps it consumes, so each piece runs on the lane of its multiexp as soon as that one
+// is done (the two 256-bit variable-base products are ~2 ms of one thread each and would otherwise sit behind the join):
+//   k_proof_a  (after A):    g_a = r*delta_g1 (table) + alpha_g1 + A;  proof.a = affine(g_a);  sga = s * g_a
+//   k_proof_b1 (after B-G1): rb1 = r * (beta_g1 + B1)
+//   k_proof_b  (after B-G2): proof.b = affine(s*delta_g2 (table) + beta_g2 + B2)
+//   k_proof_c  (after all):  proof.c = affine(sga + rb1 + H + L)
+__global__ void __launch_bounds__(32) k_proof_a(const g1_xyzz_t *table_d1, const uint32_t *scal, const g1_affine_t *vk_g1 /* alpha, beta, delta */,
+                                               const g1_jac_t *res_g1, g1_jac_t *sga, g1_affine_t *proof_a, uint8_t *inf_flags) {
+    __shared__ g1_xyzz_t sm[32];
+    g1_xyzz_t t;
+    table_mul_warp<fq_t>(table_d1, scal, sm, t);
     if (threadIdx.x != 0) return;
-    if (blockIdx.x == 0) {
-        g1_affine_t a;
-        bool ok = jacobian_to_affine(ga_b1[0], a);
-        *proof_a = a;
-        inf_flags[0] = ok ? 0 : 1;
-    } else {
-        g1_jac_t c = prods[0];
-        jacobian_add(c, prods[1]);
-        jacobian_add(c, res_g1[R_H]);
-        jacobian_add(c, res_g1[R_L]);
-        g1_affine_t a;
-        bool ok = jacobian_to_affine(c, a);
-        *proof_c = a;
-        inf_flags[2] = ok ? 0 : 1;
-    }
+    t.add_mixed(vk_g1[0], false);
+    t.add(g1_xyzz_t::from_jacobian(res_g1[R_A]));
+    const g1_jac_t ga = t.to_jacobian();
+    g1_affine_t a;
+    bool ok = jacobian_to_affine(ga, a);
+    *proof_a = a;
+    inf_flags[0] = ok ? 0 : 1;
+    *sga = jacobian_mul(ga, scal + 8);
+}
+
+__global__ void __launch_bounds__(32) k_proof_b1(const uint32_t *scal, const g1_affine_t *vk_g1, const g1_jac_t *res_g1, g1_jac_t *rb1) {
+    if (threadIdx.x != 0) return;
+    g1_xyzz_t b1 = g1_xyzz_t::from_affine(vk_g1[1]);
+    b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1]));
+    *rb1 = jacobian_mul(b1.to_jacobian(), scal);
+}
+
+__global__ void __launch_bounds__(32) k_proof_b(const g2_xyzz_t *table_d2, const uint32_t *scal, const g2_affine_t *vk_g2 /* beta, delta */,
+                                               const g2_jac_t *res_g2, g2_affine_t *proof_b, uint8_t *inf_flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    g2_xyzz_t *sm = reinterpret_cast<g2_xyzz_t *>(smem_raw);
+    g2_xyzz_t t;
+    table_mul_warp<fq2_t>(table_d2, scal + 8, sm, t);
+    if (threadIdx.x != 0) return;
+    t.add_mixed(vk_g2[0], false);
+    t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2]));
+    g2_affine_t a;
+    bool ok = jacobian_to_affine(t.to_jacobian(), a);
+    *proof_b = a;
+    inf_flags[1] = ok ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(32) k_proof_c(const g1_jac_t *sga, const g1_jac_t *rb1, const g1_jac_t *res_g1, g1_affine_t *proof_c, uint8_t *inf_flags) {
+    if (threadIdx.x != 0) return;
+    g1_jac_t c = *sga;
+    jacobian_add(c, *rb1);
+    jacobian_add(c, res_g1[R_H]);
+    jacobian_add(c, res_g1[R_L]);
+    g1_affine_t a;
+    bool ok = jacobian_to_affine(c, a);
+    *proof_c = a;
+    inf_flags[2] = ok ? 0 : 1;
 }
 
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
@@ -132,21 +133,12 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     size_t o_in = take(n_all * 32), o_aux = o_in + g.n_inputs * 32;  // inputs ++ aux, contiguous
     size_t o_da = take(n_all), o_db = take(n_all);                   // [1..1] ++ a_aux_density ; b_input_density ++ b_aux_density
     size_t o_scal = take(64), o_r1 = take(R_COUNT_G1 * 144), o_r2 = take(R_COUNT_G2 * 288), o_st = take(8 * 4);
-    size_t o_mid = take(2 * 144), o_prod = take(2 * 144), o_pa = take(96), o_pb = take(192), o_pc = take(96), o_inf = take(4);
+    size_t o_mid = take(2 * 144), o_pa = take(96), o_pb = take(192), o_pc = take(96), o_inf = take(4);
     int rc = ensure_scratch(ctx, &ctx->scratch3, &ctx->scratch3_bytes, off);
     if (rc) return rc;
     char *w = (char *)ctx->scratch3;
     // ---- inputs to HBM (zero padding of a, b, c up to m as from_coeffs does)
     auto up = [&](size_t o, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(w + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
-    const size_t used = g.n_constraints * 32;
-    B200ZK_CUDA(ctx, up(o_a, g.a, used));
-    B200ZK_CUDA(ctx, up(o_b, g.b, used));
-    B200ZK_CUDA(ctx, up(o_c, g.c, used));
-    if (vec > used) {
-        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_a + used, 0, vec - used, st));
-        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_b + used, 0, vec - used, st));
-        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_c + used, 0, vec - used, st));
-    }
     B200ZK_CUDA(ctx, up(o_in, g.inputs, g.n_inputs * 32));
     B200ZK_CUDA(ctx, up(o_aux, g.aux, g.n_aux * 32));
     if (g.n_inputs) B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_da, 1, g.n_inputs, st));  // inputs have full density in A (prover.rs:148-151)
@@ -156,6 +148,16 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     B200ZK_CUDA(ctx, up(o_scal, g.r, 32));
     B200ZK_CUDA(ctx, up(o_scal + 32, g.s, 32));
 
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));  // the assignment and densities are in HBM: lanes may start
+    const size_t used = g.n_constraints * 32;
+    B200ZK_CUDA(ctx, up(o_a, g.a, used));
+    B200ZK_CUDA(ctx, up(o_b, g.b, used));
+    B200ZK_CUDA(ctx, up(o_c, g.c, used));
+    if (vec > used) {
+        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_a + used, 0, vec - used, st));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_b + used, 0, vec - used, st));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_c + used, 0, vec - used, st));
+    }
     // ---- H polynomial (prover.rs:256-287)
     if ((rc = ntt_h_poly(ctx, w + o_a, w + o_b, w + o_c, log_m, w + o_h))) return rc;
     // ---- the 8 multiexps (prover.rs:289-318)
@@ -172,19 +174,40 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
         {crs->b_g1, 0, o_in, n_all, db, &r1[R_B1]},
         {crs->b_g2, 0, o_in, n_all, db, &r2[R_B2]},
     };
-    for (int j = 0; j < n_jobs; j++) {
-        if ((rc = msm_run(ctx, jobs[j].b, jobs[j].off, w + jobs[j].src, jobs[j].n, jobs[j].d, jobs[j].out, stw + j, 0))) return rc;
-    }
-    // ---- assembly (prover.rs:326-363)
+    // The H multiexp needs the H polynomial; the other four only need the assignment, so they run beside it on the context's
+    // lanes (own stream and workspaces each) and join before the assembly.  B200ZK_PROVE_LANES=0 keeps everything on one stream.
+    int n_lanes = n_jobs - 1;
+    if (const char *e = getenv("B200ZK_PROVE_LANES")) n_lanes = std::max(0, std::min(n_jobs - 1, atoi(e)));
+    if (n_lanes && (rc = ctx_lanes(ctx, n_lanes))) return rc;
     const g1_affine_t *vk1 = (const g1_affine_t *)crs->vk;
     const g2_affine_t *vk2 = (const g2_affine_t *)((const char *)crs->vk + 3 * 96);
-    g1_jac_t *mid = (g1_jac_t *)(w + o_mid), *prod = (g1_jac_t *)(w + o_prod);
+    g1_jac_t *mid = (g1_jac_t *)(w + o_mid);  // sga, rb1
     uint8_t *dinf = (uint8_t *)(w + o_inf);
-    ctx->launches += 3;
-    k_proof_stage1<<<2, 32, 32 * sizeof(g2_xyzz_t), st>>>((const g1_xyzz_t *)crs->table_delta_g1, (const g2_xyzz_t *)crs->table_delta_g2,
-                                                         (const uint32_t *)(w + o_scal), vk1, vk2, r1, r2, mid, (g2_affine_t *)(w + o_pb), dinf);
-    k_proof_stage2<<<2, 32, 0, st>>>(mid, (const uint32_t *)(w + o_scal), prod);
-    k_proof_stage3<<<2, 32, 0, st>>>(mid, prod, r1, (g1_affine_t *)(w + o_pa), (g1_affine_t *)(w + o_pc), dinf);
+    const uint32_t *scal = (const uint32_t *)(w + o_scal);
+    for (int j = 0; j < n_jobs; j++) {
+        // job 0 (H) stays on the main stream; job j >= 1 goes to lane (j - 1) mod n_lanes
+        Ctx *on = (j == 0 || n_lanes == 0) ? ctx : ctx->lanes[(j - 1) % n_lanes];
+        std::unique_lock<std::mutex> lk;
+        if (on != ctx) {
+            lk = std::unique_lock<std::mutex>(on->mu);
+            B200ZK_CUDA(ctx, cudaStreamWaitEvent(on->stream, ctx->ev_fork, 0));
+        }
+        const unsigned long long before = on->launches;
+        if ((rc = msm_run(on, jobs[j].b, jobs[j].off, w + jobs[j].src, jobs[j].n, jobs[j].d, jobs[j].out, stw + j, 0)))
+            return on == ctx ? rc : set_error(ctx, rc, on->last_error);
+        // the piece of the assembly (prover.rs:326-363) that only needs this multiexp
+        if (j == 2) k_proof_a<<<1, 32, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, r1, mid, (g1_affine_t *)(w + o_pa), dinf);
+        if (j == 3) k_proof_b1<<<1, 32, 0, on->stream>>>(scal, vk1, r1, mid + 1);
+        if (j == 4) k_proof_b<<<1, 32, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, r2, (g2_affine_t *)(w + o_pb), dinf);
+        if (j >= 2) on->launches++;
+        if (on != ctx) ctx->launches += on->launches - before;
+    }
+    for (int l = 0; l < n_lanes; l++) {
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->lanes[l]->ev_join, ctx->lanes[l]->stream));
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->lanes[l]->ev_join, 0));
+    }
+    k_proof_c<<<1, 32, 0, st>>>(mid, mid + 1, r1, (g1_affine_t *)(w + o_pc), dinf);
+    ctx->launches++;
     B200ZK_CUDA(ctx, cudaGetLastError());
     uint32_t status[8];
     uint8_t inf3[4];

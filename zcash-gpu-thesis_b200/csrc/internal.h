@@ -63,10 +63,15 @@ struct Ctx {
     int window_override = 0;  // b200zk_set_msm_window
     unsigned long long launches = 0;  // kernels launched by this context (b200zk_launch_count)
     bool prof_on = false;        // bracket the dominant MSM kernel with events
+    // lanes: child contexts on the same device (own stream + workspaces) on which one create_proof runs its independent
+    // multiexps side by side, as prover.rs:289-318 keeps its futures in flight together; created on first use
+    std::vector<Ctx *> lanes;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
 int ensure_scratch(Ctx *ctx, void **buf, size_t *cur, size_t bytes);
+int ctx_lanes(Ctx *ctx, int n);  // make sure ctx->lanes holds n children; B200ZK_OK or an error recorded in ctx
 
 struct Bases {
     Ctx *ctx;

@@ -235,29 +235,47 @@ __global__ void __launch_bounds__(128, sizeof(F) > 48 ? 2 : B200ZK_ACC_MINBLOCKS
     *dst = acc;
 }
 
-// one warp per split bucket: lanes stride over the bucket's partial sums, then a shared-memory tree
+// Folds the partial sums of the split buckets.  Each lane of a warp takes one split bucket; a bucket with few partials
+// (small multiexps cut every chain, so most buckets have 2-4) is summed by its lane alone, one with many (bucket 1 of a
+// witness) by the whole warp: lanes stride over its partials, then a shared-memory tree.
+static constexpr uint32_t SPLIT_SERIAL_MAX = 8;
 template <class F>
 __global__ void __launch_bounds__(32) k_msm_combine_split(const uint32_t *__restrict__ split_list, const uint32_t *__restrict__ n_split,
                                                          const uint32_t *__restrict__ task_cnt, const uint32_t *__restrict__ task_off,
                                                          const XYZZ<F> *__restrict__ partials, XYZZ<F> *__restrict__ buckets) {
     __shared__ XYZZ<F> sm[32];
     const uint32_t total = *n_split;
-    for (uint32_t s = blockIdx.x; s < total; s += gridDim.x) {
-        uint32_t b = split_list[s], cnt = task_cnt[b], off = task_off[b];
-        XYZZ<F> acc = XYZZ<F>::zero();
-        for (uint32_t j = threadIdx.x; j < cnt; j += 32) acc.add(partials[off + j]);
-        sm[threadIdx.x] = acc;
-        __syncthreads();
-        for (uint32_t stride = 16; stride > 0; stride >>= 1) {
-            if (threadIdx.x < stride) {
-                XYZZ<F> t = sm[threadIdx.x];
-                t.add(sm[threadIdx.x + stride]);
-                sm[threadIdx.x] = t;
+    for (uint32_t base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+        const uint32_t s = base + threadIdx.x;
+        const bool valid = s < total;
+        uint32_t b = 0, cnt = 0, off = 0;
+        if (valid) { b = split_list[s]; cnt = task_cnt[b]; off = task_off[b]; }
+        const bool big = valid && cnt > SPLIT_SERIAL_MAX;
+        if (valid && !big) {
+            XYZZ<F> acc = partials[off];
+            for (uint32_t j = 1; j < cnt; j++) acc.add(partials[off + j]);
+            buckets[b] = acc;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, big);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t bb = __shfl_sync(0xffffffffu, b, src), cc = __shfl_sync(0xffffffffu, cnt, src), oo = __shfl_sync(0xffffffffu, off, src);
+            XYZZ<F> acc = XYZZ<F>::zero();
+            for (uint32_t j = threadIdx.x; j < cc; j += 32) acc.add(partials[oo + j]);
+            sm[threadIdx.x] = acc;
+            __syncthreads();
+            for (uint32_t stride = 16; stride > 0; stride >>= 1) {
+                if (threadIdx.x < stride) {
+                    XYZZ<F> t = sm[threadIdx.x];
+                    t.add(sm[threadIdx.x + stride]);
+                    sm[threadIdx.x] = t;
+                }
+                __syncthreads();
             }
+            if (threadIdx.x == 0) buckets[bb] = sm[0];
             __syncthreads();
         }
-        if (threadIdx.x == 0) buckets[b] = sm[0];
-        __syncthreads();
     }
 }
 
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(64) k_msm_reduce_level(const XYZZ<F> *__restri
 // per level; a single thread needs ~10 us per point addition, so small multiexps (a Sapling proof's are ~10^5 points) were
 // spending most of their time here.  sum_i i R_i = sum_j 2^j T_j with T_j = sum over {i : bit j of i} R_i: all T_j, sum R_i and
 // sum A_i are plain sums, computed together by log8(n) levels of <= 8 additions (k_msm_slice_sum), then one short Horner.
-static constexpr uint32_t SLICE_MAX = 32768;
+static constexpr uint32_t SLICE_MAX = 4096;
 // slice s < nb: masked sum of R (bit s of the index); s == nb: sum of R; s == nb + 1: sum of A.
 // first level: in = R / A arrays of n_in entries per window; later levels: in = previous Y ((nb + 2) rows of n_in per window)
 template <class F>
@@ -412,7 +430,18 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_buckets = take(nbk * sizeof(XYZZ<F>));
     // bucket splitting: cap = 2 x mean bucket load + 32; at most n*W/cap + nbk... split tasks, bounded by 2*n*W/cap
     const size_t mean_load = n_exp * (sh.W / bw) / sh.B;
-    const uint32_t cap = (uint32_t)(mean_load + mean_load / 2 + 32);  // chains longer than ~1.5 x the mean are split
+    uint32_t cap = (uint32_t)(mean_load + mean_load / 2 + 32);  // chains longer than ~1.5 x the mean are split
+    {
+        // A small multiexp cannot fill the machine with one thread per bucket: its time is (longest chain) x (latency of one
+        // dependent point addition).  Cut the chains so that there are about `waves` tasks per resident thread slot.
+        double waves = 2.0;
+        if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
+        const size_t slots = (size_t)ctx->sm_count * (sizeof(F) > 48 ? 2 : 3) * 128;
+        if (waves > 0) {
+            const size_t fill = (size_t)((double)(n_exp * sh.W) / (waves * (double)slots));
+            cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(8, fill));
+        }
+    }
     const size_t max_tasks = (size_t)2 * n_exp * sh.W / cap + 2;
     size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
     size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
@@ -420,7 +449,9 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t lvl_entries = (size_t)bw * ((sh.B + RED_K - 1) / RED_K) + bw;
     size_t o_r0 = take(lvl_entries * sizeof(XYZZ<F>)), o_a0 = take(lvl_entries * sizeof(XYZZ<F>));
     size_t o_r1 = take(lvl_entries * sizeof(XYZZ<F>)), o_a1 = take(lvl_entries * sizeof(XYZZ<F>));
-    const size_t slice_n = std::min<size_t>(sh.B, SLICE_MAX);
+    uint32_t slice_max = SLICE_MAX;
+    if (const char *e = getenv("B200ZK_SLICE_MAX")) slice_max = (uint32_t)std::max(8, atoi(e));
+    const size_t slice_n = std::min<size_t>(sh.B, slice_max);
     const size_t y_entries = (size_t)bw * 18 * ((slice_n + 7) / 8) + 64;  // (nb + 2 <= 17) rows of n/8 sums per window
     size_t o_y0 = take(y_entries * sizeof(XYZZ<F>)), o_y1 = take((y_entries / 8 + 64 * (size_t)bw * 18) * sizeof(XYZZ<F>));
     // batched-affine accumulation (msm_batched_affine.cuh): correct (the whole MSM suite passes with B200ZK_BA=1) but, as
@@ -480,7 +511,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     const XYZZ<F> *inR = buckets, *inA = nullptr;
     uint32_t n_in = sh.B, log_len = 0;
     int pp = 0;
-    while (n_in > SLICE_MAX) {
+    while (n_in > slice_max) {
         uint32_t n_out = (n_in + RED_K - 1) / RED_K;
         uint32_t threads = n_out * bw;
         k_msm_reduce_level<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, n_in, lr[pp], la[pp], n_out, bw, log_len);
