@@ -66,6 +66,7 @@ struct Ctx {
     // lanes: child contexts on the same device (own stream + workspaces) on which one create_proof runs its independent
     // multiexps side by side, as prover.rs:289-318 keeps its futures in flight together; created on first use
     std::vector<Ctx *> lanes;
+    bool combine_smem_opt_in[2] = {false, false};  // k_msm_combine_big<G1/G2> allowed its dynamic shared memory on this device
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };

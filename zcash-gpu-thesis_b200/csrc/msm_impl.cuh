@@ -172,9 +172,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
 #ifndef B200ZK_ACC_MINBLOCKS
 #define B200ZK_ACC_MINBLOCKS 3
 #endif
+#ifndef B200ZK_ACC_MINBLOCKS_G2
+#define B200ZK_ACC_MINBLOCKS_G2 2
+#endif
 // Oversized buckets (witness scalars are full of 0/1/small values: half of a Sapling witness lands in bucket 1 of
 // window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
 // split bucket are folded by one warp (k_msm_combine_split).  Uniform scalars never split (cap = 2 x mean + slack).
+static constexpr uint32_t SPLIT_SERIAL_MAX = 8;
 static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, uint32_t n_buckets, uint32_t cap, uint32_t *__restrict__ task_cnt,
                                          uint32_t *__restrict__ split_list, uint32_t *__restrict__ n_split, uint32_t *__restrict__ size_hist) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,7 +186,9 @@ static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, u
     uint32_t cnt = offsets[b + 1] - offsets[b];
     uint32_t tasks = cnt <= cap ? 0u : (cnt + cap - 1) / cap;
     task_cnt[b] = tasks;
-    if (tasks) split_list[atomicAdd(n_split, 1u)] = b;
+    // n_split[0]: buckets with a few partial sums, listed from the front; n_split[1]: buckets with many, listed from the back
+    if (tasks > SPLIT_SERIAL_MAX) split_list[n_buckets - 1 - atomicAdd(n_split + 1, 1u)] = b;
+    else if (tasks) split_list[atomicAdd(n_split, 1u)] = b;
     atomicAdd(&size_hist[cap - min(cnt, cap)], 1u);  // key 0 = fullest
 }
 // Counting sort of the bucket ids by load (fullest first): the 32 buckets of a warp then carry (almost) the same number of
@@ -196,7 +202,7 @@ static __global__ void k_msm_order_buckets(const uint32_t *__restrict__ offsets,
 }
 
 template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) > 48 ? 2 : B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128, sizeof(F) > 48 ? B200ZK_ACC_MINBLOCKS_G2 : B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                        const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
                                                        const uint32_t *__restrict__ task_off, const uint32_t *__restrict__ order, uint32_t cap,
                                                        uint32_t max_tasks, XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ partials) {
@@ -235,47 +241,46 @@ __global__ void __launch_bounds__(128, sizeof(F) > 48 ? 2 : B200ZK_ACC_MINBLOCKS
     *dst = acc;
 }
 
-// Folds the partial sums of the split buckets.  Each lane of a warp takes one split bucket; a bucket with few partials
-// (small multiexps cut every chain, so most buckets have 2-4) is summed by its lane alone, one with many (bucket 1 of a
-// witness) by the whole warp: lanes stride over its partials, then a shared-memory tree.
-static constexpr uint32_t SPLIT_SERIAL_MAX = 8;
+// Folds the partial sums of the split buckets.  A bucket with few partials (small multiexps cut every chain, so most
+// buckets have 2-4) is summed by one thread; one with many (bucket 1 of a witness, the few buckets the short top window
+// feeds) by a whole block: threads stride over its partials, then a shared-memory tree.
 template <class F>
-__global__ void __launch_bounds__(32) k_msm_combine_split(const uint32_t *__restrict__ split_list, const uint32_t *__restrict__ n_split,
+__global__ void __launch_bounds__(64) k_msm_combine_small(const uint32_t *__restrict__ split_list, const uint32_t *__restrict__ n_split,
                                                          const uint32_t *__restrict__ task_cnt, const uint32_t *__restrict__ task_off,
                                                          const XYZZ<F> *__restrict__ partials, XYZZ<F> *__restrict__ buckets) {
-    __shared__ XYZZ<F> sm[32];
-    const uint32_t total = *n_split;
-    for (uint32_t base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
-        const uint32_t s = base + threadIdx.x;
-        const bool valid = s < total;
-        uint32_t b = 0, cnt = 0, off = 0;
-        if (valid) { b = split_list[s]; cnt = task_cnt[b]; off = task_off[b]; }
-        const bool big = valid && cnt > SPLIT_SERIAL_MAX;
-        if (valid && !big) {
-            XYZZ<F> acc = partials[off];
-            for (uint32_t j = 1; j < cnt; j++) acc.add(partials[off + j]);
-            buckets[b] = acc;
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, big);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t bb = __shfl_sync(0xffffffffu, b, src), cc = __shfl_sync(0xffffffffu, cnt, src), oo = __shfl_sync(0xffffffffu, off, src);
-            XYZZ<F> acc = XYZZ<F>::zero();
-            for (uint32_t j = threadIdx.x; j < cc; j += 32) acc.add(partials[oo + j]);
-            sm[threadIdx.x] = acc;
-            __syncthreads();
-            for (uint32_t stride = 16; stride > 0; stride >>= 1) {
-                if (threadIdx.x < stride) {
-                    XYZZ<F> t = sm[threadIdx.x];
-                    t.add(sm[threadIdx.x + stride]);
-                    sm[threadIdx.x] = t;
-                }
-                __syncthreads();
+    const uint32_t total = n_split[0];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
+        const uint32_t b = split_list[s], cnt = task_cnt[b], off = task_off[b];
+        XYZZ<F> acc = partials[off];
+        for (uint32_t j = 1; j < cnt; j++) acc.add(partials[off + j]);
+        buckets[b] = acc;
+    }
+}
+static constexpr uint32_t COMBINE_BIG_THREADS = 256;
+template <class F>
+__global__ void __launch_bounds__(COMBINE_BIG_THREADS) k_msm_combine_big(const uint32_t *__restrict__ split_list, const uint32_t *__restrict__ n_split,
+                                                                        uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
+                                                                        const uint32_t *__restrict__ task_off, const XYZZ<F> *__restrict__ partials,
+                                                                        XYZZ<F> *__restrict__ buckets) {
+    extern __shared__ __align__(16) unsigned char combine_smem[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(combine_smem);
+    const uint32_t total = n_split[1];
+    for (uint32_t s = blockIdx.x; s < total; s += gridDim.x) {
+        const uint32_t b = split_list[n_buckets - 1 - s], cnt = task_cnt[b], off = task_off[b];
+        XYZZ<F> acc = XYZZ<F>::zero();
+        for (uint32_t j = threadIdx.x; j < cnt; j += COMBINE_BIG_THREADS) acc.add(partials[off + j]);
+        sm[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t stride = COMBINE_BIG_THREADS / 2; stride > 0; stride >>= 1) {
+            if (threadIdx.x < stride && threadIdx.x + stride < cnt) {
+                XYZZ<F> t = sm[threadIdx.x];
+                t.add(sm[threadIdx.x + stride]);
+                sm[threadIdx.x] = t;
             }
-            if (threadIdx.x == 0) buckets[bb] = sm[0];
             __syncthreads();
         }
+        if (threadIdx.x == 0) buckets[b] = sm[0];
+        __syncthreads();
     }
 }
 
@@ -420,7 +425,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     // workspace carve-up
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_status = take(4 * sizeof(uint32_t));
+    size_t o_status = take(8 * sizeof(uint32_t));
     size_t o_counts = take((nbk + 1) * sizeof(uint32_t));
     size_t o_offsets = take((nbk + 1) * sizeof(uint32_t));
     size_t o_cursor = take((nbk + 1) * sizeof(uint32_t));
@@ -436,7 +441,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         // dependent point addition).  Cut the chains so that there are about `waves` tasks per resident thread slot.
         double waves = 2.0;
         if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
-        const size_t slots = (size_t)ctx->sm_count * (sizeof(F) > 48 ? 2 : 3) * 128;
+        const size_t slots = (size_t)ctx->sm_count * (sizeof(F) > 48 ? B200ZK_ACC_MINBLOCKS_G2 : B200ZK_ACC_MINBLOCKS) * 128;
         if (waves > 0) {
             const size_t fill = (size_t)((double)(n_exp * sh.W) / (waves * (double)slots));
             cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(8, fill));
@@ -494,17 +499,24 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         ctx->launches += 3;
         if ((rc = ba_accumulate<F>(ctx, (const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk, refs_bound, buckets, ws + o_ba, scan))) return rc;
     } else {
-        uint32_t *n_split = status + 3;
-        B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, sizeof(uint32_t), st));
+        uint32_t *n_split = status + 4;  // two counters: few-partial buckets, many-partial buckets
+        B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, 2 * sizeof(uint32_t), st));
         B200ZK_CUDA(ctx, cudaMemsetAsync(size_hist, 0, (cap + 2) * sizeof(uint32_t), st));
         k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split, size_hist);
         ctx->launches += scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
         ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
-        ctx->launches += 7;  // digits x2, count_tasks, order_buckets, accumulate, combine_split, window_combine
+        ctx->launches += 8;  // digits x2, count_tasks, order_buckets, accumulate, combine_small, combine_big, window_combine
         k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
         k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
                                                                                       task_cnt, task_off, order, cap, (uint32_t)max_tasks, buckets, partials);
-        k_msm_combine_split<F><<<2048, 32, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
+        k_msm_combine_small<F><<<1024, 64, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
+        const size_t big_smem = COMBINE_BIG_THREADS * sizeof(XYZZ<F>);  // 48 KiB (G1) / 96 KiB (G2) of dynamic shared memory
+        bool &opted_in = ctx->combine_smem_opt_in[sizeof(F) > 48 ? 1 : 0];
+        if (!opted_in) {
+            B200ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_combine_big<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
+            opted_in = true;
+        }
+        k_msm_combine_big<F><<<256, COMBINE_BIG_THREADS, big_smem, st>>>(split_list, n_split, (uint32_t)nbk, task_cnt, task_off, partials, buckets);
     }
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
     // reduction: 8-ary (R, A) tree while a window has more than SLICE_MAX entries, then the bit-sliced sums
