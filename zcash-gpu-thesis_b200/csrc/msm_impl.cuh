@@ -178,16 +178,16 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
 // Oversized buckets (witness scalars are full of 0/1/small values: half of a Sapling witness lands in bucket 1 of
 // window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
 // split bucket are folded by one warp (k_msm_combine_split).  Uniform scalars never split (cap = 2 x mean + slack).
-static constexpr uint32_t SPLIT_SERIAL_MAX = 8;
+static constexpr uint32_t SPLIT_SERIAL_MAX = 32;  // up to here one thread per bucket beats a block per bucket
 static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, uint32_t n_buckets, uint32_t cap, uint32_t *__restrict__ task_cnt,
-                                         uint32_t *__restrict__ split_list, uint32_t *__restrict__ n_split, uint32_t *__restrict__ size_hist) {
+                                         uint32_t *__restrict__ split_list, uint32_t *__restrict__ n_split, uint32_t *__restrict__ size_hist, uint32_t serial_max) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
     uint32_t cnt = offsets[b + 1] - offsets[b];
     uint32_t tasks = cnt <= cap ? 0u : (cnt + cap - 1) / cap;
     task_cnt[b] = tasks;
     // n_split[0]: buckets with a few partial sums, listed from the front; n_split[1]: buckets with many, listed from the back
-    if (tasks > SPLIT_SERIAL_MAX) split_list[n_buckets - 1 - atomicAdd(n_split + 1, 1u)] = b;
+    if (tasks > serial_max) split_list[n_buckets - 1 - atomicAdd(n_split + 1, 1u)] = b;
     else if (tasks) split_list[atomicAdd(n_split, 1u)] = b;
     atomicAdd(&size_hist[cap - min(cnt, cap)], 1u);  // key 0 = fullest
 }
@@ -499,10 +499,12 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         ctx->launches += 3;
         if ((rc = ba_accumulate<F>(ctx, (const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk, refs_bound, buckets, ws + o_ba, scan))) return rc;
     } else {
+        uint32_t serial_max = SPLIT_SERIAL_MAX;
+        if (const char *e = getenv("B200ZK_SPLIT_SERIAL_MAX")) serial_max = (uint32_t)atoi(e);
         uint32_t *n_split = status + 4;  // two counters: few-partial buckets, many-partial buckets
         B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, 2 * sizeof(uint32_t), st));
         B200ZK_CUDA(ctx, cudaMemsetAsync(size_hist, 0, (cap + 2) * sizeof(uint32_t), st));
-        k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split, size_hist);
+        k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split, size_hist, serial_max);
         ctx->launches += scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
         ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
         ctx->launches += 8;  // digits x2, count_tasks, order_buckets, accumulate, combine_small, combine_big, window_combine
