@@ -1,0 +1,12 @@
+"""Device timeline of one Spend-shaped create_proof: B200ZK_PROVE_TRACE=1 python tools/prove_trace.py"""
+import os, sys
+os.environ.setdefault("B200ZK_PROVE_TRACE", "1")
+os.environ["B200ZK_SPEND_STREAMS"] = "1"
+os.environ["B200ZK_SPEND_PER_STREAM"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+import zcash_gpu_thesis_b200 as zk
+
+w = zk.Worker(0)
+print(bench.bench_spend_proofs(w, zk, np.random.default_rng(5), 1))

@@ -11,7 +11,9 @@
 // r*delta_g1 and s*delta_g2 use per-CRS window tables (32 windows x 255 multiples, built once at upload, summed by a
 // warp tree); the two variable-base products are MSB-first double-and-add with the reference's Jacobian formulas.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "ec.cuh"
 #include "internal.h"
@@ -114,6 +116,29 @@ __global__ void __launch_bounds__(32) k_proof_c(const g1_jac_t *sga, const g1_ja
 
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
+// B200ZK_PROVE_TRACE=1: device timeline of one create_proof (events on the main stream and the lanes), printed to stderr
+struct ProveTrace {
+    bool on = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    ProveTrace() { if (const char *e = getenv("B200ZK_PROVE_TRACE")) on = e[0] == '1'; }
+    void mark(const char *name, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        marks.emplace_back(name, ev);
+    }
+    void report() {
+        if (!on || marks.empty()) return;
+        for (auto &m : marks) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[0].second, m.second);
+            fprintf(stderr, "[prove] %-22s %8.3f ms\n", m.first, ms);
+        }
+        for (auto &m : marks) cudaEventDestroy(m.second);
+    }
+};
+
 int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c, uint8_t *inf_flags) {
     cudaStream_t st = ctx->stream;
     if (crs->subverted) return set_error(ctx, B200ZK_ERR_UNEXPECTED_IDENTITY, "delta_g1 / delta_g2 is the identity (subversion check, prover.rs:320-324)");
@@ -138,6 +163,8 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     if (rc) return rc;
     char *w = (char *)ctx->scratch3;
     // ---- inputs to HBM (zero padding of a, b, c up to m as from_coeffs does)
+    ProveTrace trace;
+    trace.mark("start", st);
     auto up = [&](size_t o, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(w + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
     B200ZK_CUDA(ctx, up(o_in, g.inputs, g.n_inputs * 32));
     B200ZK_CUDA(ctx, up(o_aux, g.aux, g.n_aux * 32));
@@ -149,6 +176,7 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     B200ZK_CUDA(ctx, up(o_scal + 32, g.s, 32));
 
     B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));  // the assignment and densities are in HBM: lanes may start
+    trace.mark("assignment uploaded", st);
     const size_t used = g.n_constraints * 32;
     B200ZK_CUDA(ctx, up(o_a, g.a, used));
     B200ZK_CUDA(ctx, up(o_b, g.b, used));
@@ -158,8 +186,10 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
         B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_b + used, 0, vec - used, st));
         B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_c + used, 0, vec - used, st));
     }
+    trace.mark("a, b, c uploaded", st);
     // ---- H polynomial (prover.rs:256-287)
     if ((rc = ntt_h_poly(ctx, w + o_a, w + o_b, w + o_c, log_m, w + o_h))) return rc;
+    trace.mark("h polynomial", st);
     // ---- the 8 multiexps (prover.rs:289-318)
     g1_jac_t *r1 = (g1_jac_t *)(w + o_r1);
     g2_jac_t *r2 = (g2_jac_t *)(w + o_r2);
@@ -195,19 +225,24 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
         const unsigned long long before = on->launches;
         if ((rc = msm_run(on, jobs[j].b, jobs[j].off, w + jobs[j].src, jobs[j].n, jobs[j].d, jobs[j].out, stw + j, 0)))
             return on == ctx ? rc : set_error(ctx, rc, on->last_error);
+        static const char *const msm_names[] = {"multiexp H", "multiexp L", "multiexp A", "multiexp B-G1", "multiexp B-G2"};
+        static const char *const piece_names[] = {"", "", "piece a (g_a, s*g_a)", "piece b1 (r*B1)", "piece b (g_b)"};
+        trace.mark(msm_names[j], on->stream);
         // the piece of the assembly (prover.rs:326-363) that only needs this multiexp
         if (j == 2) k_proof_a<<<1, 32, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, r1, mid, (g1_affine_t *)(w + o_pa), dinf);
         if (j == 3) k_proof_b1<<<1, 32, 0, on->stream>>>(scal, vk1, r1, mid + 1);
         if (j == 4) k_proof_b<<<1, 32, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, r2, (g2_affine_t *)(w + o_pb), dinf);
-        if (j >= 2) on->launches++;
+        if (j >= 2) { on->launches++; trace.mark(piece_names[j], on->stream); }
         if (on != ctx) ctx->launches += on->launches - before;
     }
     for (int l = 0; l < n_lanes; l++) {
         B200ZK_CUDA(ctx, cudaEventRecord(ctx->lanes[l]->ev_join, ctx->lanes[l]->stream));
         B200ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->lanes[l]->ev_join, 0));
     }
+    trace.mark("join", st);
     k_proof_c<<<1, 32, 0, st>>>(mid, mid + 1, r1, (g1_affine_t *)(w + o_pc), dinf);
     ctx->launches++;
+    trace.mark("piece c", st);
     B200ZK_CUDA(ctx, cudaGetLastError());
     uint32_t status[8];
     uint8_t inf3[4];
@@ -217,6 +252,7 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     B200ZK_CUDA(ctx, cudaMemcpyAsync(inf3, dinf, 3, cudaMemcpyDeviceToHost, st));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(status, stw, sizeof(status), cudaMemcpyDeviceToHost, st));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
+    trace.report();
     for (int j = 0; j < n_jobs; j++) {
         if (status[j] == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status[j], "UnexpectedIdentity in multiexp");
         if (status[j] == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status[j], "IoError(UnexpectedEof) in multiexp");
