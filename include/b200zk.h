@@ -125,6 +125,13 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
  * synchronous call's return value; pass NULL to ignore. */
 int b200zk_multiexp_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp,
                         const uint8_t *d_density, void *d_out_jacobian, void *d_status);
+/* `batch` multiexps over the same bases in one pipeline (the multiexps of `batch` proofs over one CRS, or the futures
+ * prover.rs:289-318 holds together): exponent vector k starts k * scalar_stride exponents after d_scalars, density map k
+ * (if any) k * density_stride bytes after d_density; each has n_exp exponents and starts at base_offset.  Results: `batch`
+ * consecutive Jacobian points in d_out_jacobians and `batch` status words in d_status (device memory, stream-ordered). */
+int b200zk_multiexp_batch_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp,
+                              size_t scalar_stride, const uint8_t *d_density, size_t density_stride, uint32_t batch, void *d_out_jacobians,
+                              void *d_status);
 /* The reference's multiexp() returns a future and the prover keeps several in flight (prover.rs:289-318, 339-354).
  * _async enqueues the host->device copy of the exponents on the context's copy stream and the multiexp behind it on the
  * compute stream, then returns; copies of later jobs overlap the computation of earlier ones.  `scalars` / `density` must
@@ -204,6 +211,25 @@ int b200zk_groth16_prove(b200zk_ctx *ctx, const b200zk_crs *crs, const uint64_t 
                          const uint64_t *inputs, size_t n_inputs, const uint64_t *aux, size_t n_aux, const uint8_t *a_aux_density,
                          const uint8_t *b_input_density, const uint8_t *b_aux_density, const uint64_t r[4], const uint64_t s[4],
                          uint64_t proof_a[12], uint64_t proof_b[24], uint64_t proof_c[12], uint8_t inf_flags[3]);
+
+/* A batch of create_proof calls over one CRS and one circuit -- what a wallet or block producer issues as a run of
+ * librustzcash_sapling_spend_proof calls (librustzcash/src/rustzcash.rs:1375; each ends in create_random_proof,
+ * sapling-crypto/src/... prover.rs:192-203).  Every proof has n_constraints / n_inputs / n_aux of the same size; the
+ * per-proof pointers have the meaning of b200zk_groth16_prove's arguments.  The proofs are proved `lockstep` at a time
+ * (0 = 8): the five multiexps of those proofs run as five batched multiexps, which fills the GPU where one 10^5-point
+ * multiexp cannot.  Outputs: n_proofs consecutive proofs (12 / 24 / 12 u64 and 3 flags each).  On an error the status
+ * is that of the first failing group; proofs of earlier groups are complete. */
+typedef struct b200zk_prove_input {
+    const uint64_t *a, *b, *c;          /* n_constraints x 4 u64, Montgomery */
+    const uint64_t *inputs, *aux;       /* n_inputs x 4, n_aux x 4 canonical FrRepr */
+    const uint8_t *a_aux_density;       /* n_aux bytes */
+    const uint8_t *b_input_density;     /* n_inputs bytes */
+    const uint8_t *b_aux_density;       /* n_aux bytes */
+    const uint64_t *r, *s;              /* 4 u64 each, canonical FrRepr */
+} b200zk_prove_input;
+int b200zk_groth16_prove_batch(b200zk_ctx *ctx, const b200zk_crs *crs, const b200zk_prove_input *proofs, size_t n_proofs, size_t n_constraints,
+                               size_t n_inputs, size_t n_aux, int lockstep, uint64_t *proofs_a, uint64_t *proofs_b, uint64_t *proofs_c,
+                               uint8_t *inf_flags);
 
 /* Per-kernel timing for the roofline report: when enabled, b200zk_multiexp(_dev) brackets its dominant kernel
  * (bucket accumulation) with CUDA events on the context's stream; read() synchronises and returns the summed

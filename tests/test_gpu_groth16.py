@@ -116,6 +116,37 @@ def test_create_proof_matches_oracle(worker, which):
     assert not verify_proof(E, params.vk, gp, [(public[0] + 1) % Fr.p] + public[1:])
 
 
+def test_batched_proofs_equal_single_proofs(worker):
+    """b200zk_groth16_prove_batch: proofs of one circuit proved in lock-step (groups of 3 here: 3 + 2) are the proofs
+    create_proof gives one at a time, for different witnesses and different (r, s)."""
+    import zcash_gpu_thesis_b200 as zk
+
+    E = BlsEngine
+    r0 = util.rng(2100)
+    rnd = lambda: util.rows_to_ints(util.random_fr_repr(r0, 1))[0]
+    consts = [rnd() for _ in range(16)]
+    params, _ = generate_parameters(E, MiMCLike(0, 0, consts), G1.gen, G2.gen, *[rnd() for _ in range(5)])
+    dev = _upload(worker, params)
+    mont = lambda v: np.array([Fr.to_mont_limbs(x) for x in v], dtype=np.uint64).reshape(len(v), 4)
+    rep = lambda v: np.array([int_to_limbs(x, 4) for x in v], dtype=np.uint64).reshape(len(v), 4)
+    batch, wants = [], []
+    for _ in range(5):
+        asg = synthesize_assignment(E, MiMCLike(rnd(), rnd(), consts))
+        r, s = rnd(), rnd()
+        wants.append(prove_from_assignment(E, asg, params, r, s))
+        batch.append((mont(asg.a), mont(asg.b), mont(asg.c), rep(asg.input_assignment), rep(asg.aux_assignment), asg.a_aux_density,
+                      asg.b_input_density, asg.b_aux_density, r, s))
+    proofs = zk.create_proofs_from_assignments(worker, dev, batch, lockstep=3)
+    assert len(proofs) == 5
+    for got, want in zip(proofs, wants):
+        assert got.write(worker) == proof_bytes(want)
+    one = zk.create_proof_from_assignment(worker, dev, *batch[3])
+    assert one.write(worker) == proofs[3].write(worker)
+    assert zk.create_proofs_from_assignments(worker, dev, []) == []
+    with pytest.raises(ValueError):
+        zk.create_proofs_from_assignments(worker, dev, [batch[0], tuple(x[:-1] for x in batch[1][:3]) + batch[1][3:]])  # fewer constraints
+
+
 def test_subversion_check(worker):
     """prover.rs:320-324: delta at infinity -> UnexpectedIdentity."""
     import zcash_gpu_thesis_b200 as zk

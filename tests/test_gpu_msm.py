@@ -324,3 +324,52 @@ def test_batched_affine_path_matches(worker, monkeypatch):
     assert np.array_equal(zk.into_affine(worker, zk.G1, got)[0], zk.into_affine(worker, zk.G1, want)[0])
     st, ref = cref.multiexp("g1", xy, exps)
     assert st == 0 and np.array_equal(zk.into_affine(worker, zk.G1, got)[0][0], cref.into_affine("g1", ref)[0])
+
+
+@pytest.mark.parametrize("group,n,K,pre", [("g1", 0, 3, None), ("g1", 1, 2, None), ("g1", 777, 5, None), ("g1", 3000, 4, 0), ("g1", 1 << 13, 3, 12),
+                                           ("g2", 500, 3, None), ("g2", 900, 4, 0)])
+def test_batched_multiexps_equal_separate_ones(worker, group, n, K, pre):
+    """b200zk_multiexp_batch_dev: K multiexps over the same bases as bucket sets of one pipeline == K separate multiexps
+    (different exponents, different density maps, witness-like and uniform scalars mixed)."""
+    import zcash_gpu_thesis_b200 as zk
+
+    code = zk.G1 if group == "g1" else zk.G2
+    r = util.rng(4100 + n + K)
+    xy, _ = util.random_bases(group, r, n + 20)
+    bases = zk.Bases(worker, code, xy)
+    if pre is not None:
+        bases.precompute(pre)
+    exps = np.stack([util.random_fr_repr(r, n) for _ in range(K)]) if n else np.zeros((K, 0, 4), np.uint64)
+    if n > 10:
+        exps[0, 0] = int_to_limbs(Fr.p - 1, 4)
+        exps[1, 5] = 0
+        mask = r.random(n) < 0.6  # proof 1 of the batch has a witness-like vector
+        exps[1, mask] = 0
+        exps[1, mask, 0] = r.integers(0, 2, size=int(mask.sum()), dtype=np.uint64)
+    for dens in (None, [(r.random(n) < 0.3 + 0.1 * k).astype(np.uint8) for k in range(K)]):
+        got = zk.multiexp_batch(worker, (bases, 7), dens, exps)
+        for k in range(K):
+            st, want = cref.multiexp(group, xy, exps[k], density=None if dens is None else dens[k], base_offset=7)
+            assert st == 0
+            got_aff, got_inf = zk.into_affine(worker, code, got[k])
+            want_aff, want_inf = cref.into_affine(group, want)
+            assert bool(got_inf[0]) == want_inf and np.array_equal(got_aff[0], want_aff), (k, dens is None)
+
+
+def test_batched_multiexp_reports_the_failing_member(worker):
+    import zcash_gpu_thesis_b200 as zk
+
+    r = util.rng(4200)
+    xy, _ = util.random_bases("g1", r, 100)
+    inf = np.zeros(100, np.uint8)
+    inf[40] = 1
+    bases = zk.Bases(worker, zk.G1, xy, inf)
+    exps = np.stack([util.random_fr_repr(r, 60) for _ in range(3)])
+    exps[:, 40] = 0  # nobody consumes the identity base: fine
+    assert zk.multiexp_batch(worker, bases, None, exps).shape == (3, 18)
+    exps[2, 40] = (5, 0, 0, 0)
+    with pytest.raises(zk.UnexpectedIdentity, match="multiexp 2"):
+        zk.multiexp_batch(worker, bases, None, exps)
+    exps[2, 40] = 0
+    with pytest.raises(zk.IoError, match="multiexp 0"):
+        zk.multiexp_batch(worker, (bases, 50), None, exps)  # 60 exponents, 50 bases left

@@ -23,6 +23,7 @@ from .bellman import (  # noqa: F401
     Proof,
     Worker,
     create_proof_from_assignment,
+    create_proofs_from_assignments,
     decode_points,
     encode_points,
     field_vec,
@@ -31,6 +32,7 @@ from .bellman import (  # noqa: F401
     into_affine,
     multiexp,
     multiexp_async,
+    multiexp_batch,
     ntt_host,
     point_op,
 )

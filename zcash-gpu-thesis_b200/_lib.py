@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200zk_bases_free": (None, [_vp]),
     "b200zk_multiexp": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "b200zk_multiexp_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "b200zk_multiexp_batch_dev": (_i, [_vp, _vp, _sz, _vp, _sz, _sz, _vp, _sz, C.c_uint32, _vp, _vp]),
     "b200zk_multiexp_async": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, C.POINTER(_vp)]),
     "b200zk_multiexp_sharded_async": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, C.POINTER(_vp)]),
     "b200zk_job_wait": (_i, [_vp, _vp]),
@@ -69,11 +70,19 @@ SIGNATURES = {
     "b200zk_crs_create": (_i, [_vp] * 12 + [C.POINTER(_vp)]),
     "b200zk_crs_free": (None, [_vp]),
     "b200zk_groth16_prove": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200zk_groth16_prove_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
     "b200zk_launch_count": (C.c_ulonglong, [_vp, _i]),
     "b200zk_profile_enable": (_i, [_vp, _i]),
     "b200zk_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),
     "b200zk_microbench": (_i, [_vp, _i, _i, C.POINTER(C.c_double)]),
 }
+
+
+
+class ProveInput(C.Structure):
+    """b200zk_prove_input (include/b200zk.h): the per-proof pointers of b200zk_groth16_prove_batch"""
+    _fields_ = [(name, _vp) for name in ("a", "b", "c", "inputs", "aux", "a_aux_density", "b_input_density", "b_aux_density", "r", "s")]
+
 
 _lib = None
 

@@ -344,6 +344,43 @@ def multiexp(pool: Worker, bases, density_map, exponents):
     return out
 
 
+def multiexp_batch(pool: Worker, bases, density_maps, exponents):
+    """K multiexps over the same bases in one pipeline (b200zk_multiexp_batch_dev): `exponents` is (K, n, 4) canonical FrRepr,
+    `density_maps` None (FullDensity for all) or a sequence of K DensityTracker / byte arrays.  Returns the K Jacobian
+    results, shape (K, 18) or (K, 36); raises for the first multiexp whose Source would have failed."""
+    if isinstance(bases, tuple):
+        bases, offset = bases
+    else:
+        offset = 0
+    exponents = np.ascontiguousarray(exponents, dtype=np.uint64)
+    assert exponents.ndim == 3 and exponents.shape[2] == 4
+    K, n = exponents.shape[0], exponents.shape[1]
+    words = 18 if bases.group == L.G1 else 36
+    if K == 0:
+        return np.zeros((0, words), dtype=np.uint64)
+    d_exp = pool.to_device(exponents)
+    d_den = None
+    if density_maps is not None:
+        rows = [d.as_bytes() if isinstance(d, DensityTracker) else np.ascontiguousarray(d, dtype=np.uint8) for d in density_maps]
+        assert len(rows) == K and all(r.shape[0] == n for r in rows)  # multiexp.rs:302-307
+        d_den = pool.to_device(np.stack(rows) if n else np.zeros((K, 1), np.uint8))
+    d_out, d_st = pool.alloc(K * words * 8), pool.alloc(K * 4)
+    st = pool.lib.b200zk_multiexp_batch_dev(pool.ctx, bases.handle, offset, d_exp.ptr, n, n, d_den.ptr if d_den else None, n, K, d_out.ptr, d_st.ptr)
+    if st:
+        _raise(pool, st)
+    out = d_out.download(np.uint64, K * words).reshape(K, words)
+    codes = d_st.download(np.uint32, K)
+    for x in (d_exp, d_den, d_out, d_st):
+        if x is not None:
+            x.free()
+    for k in range(K):
+        if codes[k] == L.ERR_UNEXPECTED_IDENTITY:
+            raise UnexpectedIdentity(f"multiexp {k} of the batch consumed a base at infinity")
+        if codes[k] == L.ERR_UNEXPECTED_EOF:
+            raise IoError(f"multiexp {k} of the batch ran out of bases (UnexpectedEof)")
+    return out
+
+
 class MultiexpFuture:
     """The `Box<Future<Item = G::Projective, Error = SynthesisError>>` that multiexp returns (multiexp.rs:285-295)."""
 
@@ -649,3 +686,36 @@ def create_proof_from_assignment(worker, params: Parameters, a, b, c, input_assi
     if st:
         _raise(worker, st)
     return Proof(pa, pb, pc, inf)
+
+
+def create_proofs_from_assignments(worker, params: Parameters, assignments, lockstep=0):
+    """A batch of create_proof calls over one CRS and one circuit (b200zk_groth16_prove_batch): `assignments` is a sequence of
+    (a, b, c, input_assignment, aux_assignment, a_aux_density, b_input_density, b_aux_density, r, s) tuples with the meaning of
+    create_proof_from_assignment's arguments; all of the same sizes.  Returns the list of Proofs, in order."""
+    n = len(assignments)
+    if n == 0:
+        return []
+    keep, rows = [], (L.ProveInput * n)()
+    shape = None
+    for i, (a, b, c, inputs, aux, da, dbi, dba, r, s) in enumerate(assignments):
+        a, b, c, inputs, aux = _u64(a, 4), _u64(b, 4), _u64(c, 4), _u64(inputs, 4), _u64(aux, 4)
+        dens = [d.as_bytes() if isinstance(d, DensityTracker) else np.ascontiguousarray(d, dtype=np.uint8) for d in (da, dbi, dba)]
+        assert dens[0].shape[0] == aux.shape[0] and dens[1].shape[0] == inputs.shape[0] and dens[2].shape[0] == aux.shape[0]
+        this = (a.shape[0], inputs.shape[0], aux.shape[0])
+        if shape is None:
+            shape = this
+        elif this != shape or b.shape[0] != shape[0] or c.shape[0] != shape[0]:
+            raise ValueError("the proofs of a batch must come from the same circuit (equal sizes)")
+        rl = np.array([(r >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+        sl = np.array([(s >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+        arrs = (a, b, c, inputs, aux, dens[0], dens[1], dens[2], rl, sl)
+        keep.append(arrs)
+        for (name, _), arr in zip(L.ProveInput._fields_, arrs):
+            setattr(rows[i], name, arr.ctypes.data)
+    pa, pb, pc = np.zeros((n, 12), np.uint64), np.zeros((n, 24), np.uint64), np.zeros((n, 12), np.uint64)
+    inf = np.zeros((n, 3), np.uint8)
+    st = worker.lib.b200zk_groth16_prove_batch(worker.ctx, params.handle, C.cast(rows, C.c_void_p), n, shape[0], shape[1], shape[2], lockstep,
+                                               _ptr(pa), _ptr(pb), _ptr(pc), _ptr(inf))
+    if st:
+        _raise(worker, st)
+    return [Proof(pa[i], pb[i], pc[i], inf[i]) for i in range(n)]

@@ -385,6 +385,22 @@ int b200zk_multiexp_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_
     return msm_run(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jacobian, d_status, ctx->window_override);
 }
 
+int b200zk_multiexp_batch_dev(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp,
+                              size_t scalar_stride, const uint8_t *d_density, size_t density_stride, uint32_t batch, void *d_out_jacobians,
+                              void *d_status) {
+    CHECK_CTX(ctx);
+    if (!bases || !d_out_jacobians || (n_exp && !d_scalars) || batch == 0) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument or empty batch");
+    if (batch > 1 && (scalar_stride < n_exp || (d_density && density_stride < n_exp)))
+        return set_error(ctx, B200ZK_ERR_BAD_ARG, "strides must be at least n_exp");
+    if (bases->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bases live on another device");
+    USE_DEVICE(ctx);
+    MsmBatch b;
+    b.K = batch;
+    b.scalar_stride = scalar_stride;
+    b.density_stride = density_stride;
+    return msm_run(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jacobians, d_status, ctx->window_override, b);
+}
+
 int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
                     const uint8_t *density, uint64_t *out_jacobian) {
     CHECK_CTX(ctx);
@@ -761,6 +777,32 @@ int b200zk_groth16_prove(b200zk_ctx *ctx, const b200zk_crs *crs, const uint64_t 
     USE_DEVICE(ctx);
     ProveArgs g{a, b, c, n_constraints, inputs, n_inputs, aux, n_aux, a_aux_density, b_input_density, b_aux_density, r, s};
     return groth16_prove(ctx, crs, g, proof_a, proof_b, proof_c, inf_flags);
+}
+
+int b200zk_groth16_prove_batch(b200zk_ctx *ctx, const b200zk_crs *crs, const b200zk_prove_input *proofs, size_t n_proofs, size_t n_constraints,
+                               size_t n_inputs, size_t n_aux, int lockstep, uint64_t *proofs_a, uint64_t *proofs_b, uint64_t *proofs_c,
+                               uint8_t *inf_flags) {
+    CHECK_CTX(ctx);
+    if (!crs || (n_proofs && (!proofs || !proofs_a || !proofs_b || !proofs_c)) || lockstep < 0 || lockstep > 256)
+        return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument or bad lockstep");
+    if (crs->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "CRS lives on another device");
+    USE_DEVICE(ctx);
+    const size_t group = lockstep ? (size_t)lockstep : 8;
+    std::vector<ProveArgs> args;
+    for (size_t first = 0; first < n_proofs; first += group) {
+        const size_t K = std::min(group, n_proofs - first);
+        args.clear();
+        for (size_t k = 0; k < K; k++) {
+            const b200zk_prove_input &p = proofs[first + k];
+            if (!p.a || !p.b || !p.c || !p.inputs || (n_aux && (!p.aux || !p.a_aux_density || !p.b_aux_density)) || !p.b_input_density || !p.r || !p.s)
+                return set_error(ctx, B200ZK_ERR_BAD_ARG, "null pointer in proof " + std::to_string(first + k));
+            args.push_back(ProveArgs{p.a, p.b, p.c, n_constraints, p.inputs, n_inputs, p.aux, n_aux, p.a_aux_density, p.b_input_density, p.b_aux_density, p.r, p.s});
+        }
+        int rc = groth16_prove_batch(ctx, crs, args.data(), (uint32_t)K, proofs_a + 12 * first, proofs_b + 24 * first, proofs_c + 12 * first,
+                                     inf_flags ? inf_flags + 3 * first : nullptr);
+        if (rc) return rc;
+    }
+    return B200ZK_OK;
 }
 
 unsigned long long b200zk_launch_count(b200zk_ctx *ctx, int reset) {

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "ec.cuh"
@@ -23,8 +24,6 @@ namespace b200zk {
 // The reference issues a_inputs / a_aux (and the B pairs) as separate multiexps over the *same* base vector with the aux
 // cursor starting right after the inputs (groth16/mod.rs:456-481); only their sums are used (prover.rs:339-347), so each
 // pair is one multiexp over inputs ++ aux with the concatenated density map.
-enum { R_H = 0, R_L, R_A, R_B1, R_COUNT_G1 };  // G1 multiexp results (Jacobian, 144 B each)
-enum { R_B2 = 0, R_COUNT_G2 };                  // G2 result (288 B)
 
 // scal[0] = r, scal[1] = s  (canonical FrRepr, 8 u32 each)
 // block 0: T = r * delta_g1 (table), g_a = T + alpha_g1 + a_in + a_aux ; B1 = beta_g1 + b1_in + b1_aux
@@ -64,54 +63,61 @@ __device__ g1_jac_t jacobian_mul(const g1_jac_t &p, const uint32_t *k) {
 //   k_proof_b1 (after B-G1): rb1 = r * (beta_g1 + B1)
 //   k_proof_b  (after B-G2): proof.b = affine(s*delta_g2 (table) + beta_g2 + B2)
 //   k_proof_c  (after all):  proof.c = affine(sga + rb1 + H + L)
+// One block per proof of the batch (blockIdx.x = k): scal[16 k ..] = r_k, s_k; every result array is indexed by k.
 __global__ void __launch_bounds__(32) k_proof_a(const g1_xyzz_t *table_d1, const uint32_t *scal, const g1_affine_t *vk_g1 /* alpha, beta, delta */,
-                                               const g1_jac_t *res_g1, g1_jac_t *sga, g1_affine_t *proof_a, uint8_t *inf_flags) {
+                                               const g1_jac_t *res_a, g1_jac_t *sga, g1_affine_t *proof_a, uint8_t *inf_flags) {
     __shared__ g1_xyzz_t sm[32];
+    const uint32_t k = blockIdx.x;
+    scal += 16 * k;
     g1_xyzz_t t;
     table_mul_warp<fq_t>(table_d1, scal, sm, t);
     if (threadIdx.x != 0) return;
     t.add_mixed(vk_g1[0], false);
-    t.add(g1_xyzz_t::from_jacobian(res_g1[R_A]));
+    t.add(g1_xyzz_t::from_jacobian(res_a[k]));
     const g1_jac_t ga = t.to_jacobian();
     g1_affine_t a;
     bool ok = jacobian_to_affine(ga, a);
-    *proof_a = a;
-    inf_flags[0] = ok ? 0 : 1;
-    *sga = jacobian_mul(ga, scal + 8);
+    proof_a[k] = a;
+    inf_flags[4 * k + 0] = ok ? 0 : 1;
+    sga[k] = jacobian_mul(ga, scal + 8);
 }
 
-__global__ void __launch_bounds__(32) k_proof_b1(const uint32_t *scal, const g1_affine_t *vk_g1, const g1_jac_t *res_g1, g1_jac_t *rb1) {
+__global__ void __launch_bounds__(32) k_proof_b1(const uint32_t *scal, const g1_affine_t *vk_g1, const g1_jac_t *res_b1, g1_jac_t *rb1) {
     if (threadIdx.x != 0) return;
+    const uint32_t k = blockIdx.x;
     g1_xyzz_t b1 = g1_xyzz_t::from_affine(vk_g1[1]);
-    b1.add(g1_xyzz_t::from_jacobian(res_g1[R_B1]));
-    *rb1 = jacobian_mul(b1.to_jacobian(), scal);
+    b1.add(g1_xyzz_t::from_jacobian(res_b1[k]));
+    rb1[k] = jacobian_mul(b1.to_jacobian(), scal + 16 * k);
 }
 
 __global__ void __launch_bounds__(32) k_proof_b(const g2_xyzz_t *table_d2, const uint32_t *scal, const g2_affine_t *vk_g2 /* beta, delta */,
-                                               const g2_jac_t *res_g2, g2_affine_t *proof_b, uint8_t *inf_flags) {
+                                               const g2_jac_t *res_b2, g2_affine_t *proof_b, uint8_t *inf_flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     g2_xyzz_t *sm = reinterpret_cast<g2_xyzz_t *>(smem_raw);
+    const uint32_t k = blockIdx.x;
     g2_xyzz_t t;
-    table_mul_warp<fq2_t>(table_d2, scal + 8, sm, t);
+    table_mul_warp<fq2_t>(table_d2, scal + 16 * k + 8, sm, t);
     if (threadIdx.x != 0) return;
     t.add_mixed(vk_g2[0], false);
-    t.add(g2_xyzz_t::from_jacobian(res_g2[R_B2]));
+    t.add(g2_xyzz_t::from_jacobian(res_b2[k]));
     g2_affine_t a;
     bool ok = jacobian_to_affine(t.to_jacobian(), a);
-    *proof_b = a;
-    inf_flags[1] = ok ? 0 : 1;
+    proof_b[k] = a;
+    inf_flags[4 * k + 1] = ok ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(32) k_proof_c(const g1_jac_t *sga, const g1_jac_t *rb1, const g1_jac_t *res_g1, g1_affine_t *proof_c, uint8_t *inf_flags) {
+__global__ void __launch_bounds__(32) k_proof_c(const g1_jac_t *sga, const g1_jac_t *rb1, const g1_jac_t *res_h, const g1_jac_t *res_l,
+                                               g1_affine_t *proof_c, uint8_t *inf_flags) {
     if (threadIdx.x != 0) return;
-    g1_jac_t c = *sga;
-    jacobian_add(c, *rb1);
-    jacobian_add(c, res_g1[R_H]);
-    jacobian_add(c, res_g1[R_L]);
+    const uint32_t k = blockIdx.x;
+    g1_jac_t c = sga[k];
+    jacobian_add(c, rb1[k]);
+    jacobian_add(c, res_h[k]);
+    jacobian_add(c, res_l[k]);
     g1_affine_t a;
     bool ok = jacobian_to_affine(c, a);
-    *proof_c = a;
-    inf_flags[2] = ok ? 0 : 1;
+    proof_c[k] = a;
+    inf_flags[4 * k + 2] = ok ? 0 : 1;
 }
 
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
@@ -139,9 +145,18 @@ struct ProveTrace {
     }
 };
 
-int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c, uint8_t *inf_flags) {
+// K proofs over one CRS in lock-step (all of the same circuit: equal n_constraints / n_inputs / n_aux).  The five multiexps
+// of the K proofs run as five batched multiexps (K bucket sets each, msm_impl.cuh) so that a batch fills the machine where a
+// single 10^5-point multiexp cannot; K = 1 is groth16::create_proof as is.
+int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_t K, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c,
+                        uint8_t *inf_flags) {
     cudaStream_t st = ctx->stream;
     if (crs->subverted) return set_error(ctx, B200ZK_ERR_UNEXPECTED_IDENTITY, "delta_g1 / delta_g2 is the identity (subversion check, prover.rs:320-324)");
+    if (K == 0 || K > 256) return set_error(ctx, B200ZK_ERR_BAD_ARG, "batch must be in [1, 256]");
+    const ProveArgs &g = args[0];
+    for (uint32_t k = 1; k < K; k++)
+        if (args[k].n_constraints != g.n_constraints || args[k].n_inputs != g.n_inputs || args[k].n_aux != g.n_aux)
+            return set_error(ctx, B200ZK_ERR_BAD_ARG, "the proofs of a batch must come from the same circuit (equal sizes)");
     // EvaluationDomain::from_coeffs (domain.rs:48-81)
     size_t m = 1;
     uint32_t log_m = 0;
@@ -153,12 +168,14 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     const size_t vec = m * 32;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
-    size_t o_a = take(vec), o_b = take(vec), o_c = take(vec), o_h = take(vec);
+    // every per-proof array is K consecutive copies (stride = the size of one)
+    size_t o_a = take(K * vec), o_b = take(K * vec), o_c = take(K * vec), o_h = take(K * vec);
     const size_t n_all = g.n_inputs + g.n_aux;
-    size_t o_in = take(n_all * 32), o_aux = o_in + g.n_inputs * 32;  // inputs ++ aux, contiguous
-    size_t o_da = take(n_all), o_db = take(n_all);                   // [1..1] ++ a_aux_density ; b_input_density ++ b_aux_density
-    size_t o_scal = take(64), o_r1 = take(R_COUNT_G1 * 144), o_r2 = take(R_COUNT_G2 * 288), o_st = take(8 * 4);
-    size_t o_mid = take(2 * 144), o_pa = take(96), o_pb = take(192), o_pc = take(96), o_inf = take(4);
+    size_t o_in = take(K * n_all * 32);                      // inputs ++ aux, contiguous
+    size_t o_da = take(K * n_all), o_db = take(K * n_all);   // [1..1] ++ a_aux_density ; b_input_density ++ b_aux_density
+    size_t o_scal = take(K * 64), o_st = take(5 * K * 4);
+    size_t o_rh = take(K * 144), o_rl = take(K * 144), o_ra = take(K * 144), o_rb1 = take(K * 144), o_rb2 = take(K * 288);
+    size_t o_sga = take(K * 144), o_rb1r = take(K * 144), o_pa = take(K * 96), o_pb = take(K * 192), o_pc = take(K * 96), o_inf = take(K * 4);
     int rc = ensure_scratch(ctx, &ctx->scratch3, &ctx->scratch3_bytes, off);
     if (rc) return rc;
     char *w = (char *)ctx->scratch3;
@@ -166,52 +183,57 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
     ProveTrace trace;
     trace.mark("start", st);
     auto up = [&](size_t o, const void *src, size_t bytes) { return bytes ? cudaMemcpyAsync(w + o, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
-    B200ZK_CUDA(ctx, up(o_in, g.inputs, g.n_inputs * 32));
-    B200ZK_CUDA(ctx, up(o_aux, g.aux, g.n_aux * 32));
-    if (g.n_inputs) B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_da, 1, g.n_inputs, st));  // inputs have full density in A (prover.rs:148-151)
-    B200ZK_CUDA(ctx, up(o_da + g.n_inputs, g.a_aux_density, g.n_aux));
-    B200ZK_CUDA(ctx, up(o_db, g.b_input_density, g.n_inputs));
-    B200ZK_CUDA(ctx, up(o_db + g.n_inputs, g.b_aux_density, g.n_aux));
-    B200ZK_CUDA(ctx, up(o_scal, g.r, 32));
-    B200ZK_CUDA(ctx, up(o_scal + 32, g.s, 32));
-
-    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));  // the assignment and densities are in HBM: lanes may start
+    for (uint32_t k = 0; k < K; k++) {
+        const ProveArgs &p = args[k];
+        const size_t ok = k * n_all;
+        B200ZK_CUDA(ctx, up(o_in + ok * 32, p.inputs, p.n_inputs * 32));
+        B200ZK_CUDA(ctx, up(o_in + (ok + p.n_inputs) * 32, p.aux, p.n_aux * 32));
+        if (p.n_inputs) B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_da + ok, 1, p.n_inputs, st));  // inputs have full density in A (prover.rs:148-151)
+        B200ZK_CUDA(ctx, up(o_da + ok + p.n_inputs, p.a_aux_density, p.n_aux));
+        B200ZK_CUDA(ctx, up(o_db + ok, p.b_input_density, p.n_inputs));
+        B200ZK_CUDA(ctx, up(o_db + ok + p.n_inputs, p.b_aux_density, p.n_aux));
+        B200ZK_CUDA(ctx, up(o_scal + k * 64, p.r, 32));
+        B200ZK_CUDA(ctx, up(o_scal + k * 64 + 32, p.s, 32));
+    }
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));  // the assignments and densities are in HBM: lanes may start
     trace.mark("assignment uploaded", st);
     const size_t used = g.n_constraints * 32;
-    B200ZK_CUDA(ctx, up(o_a, g.a, used));
-    B200ZK_CUDA(ctx, up(o_b, g.b, used));
-    B200ZK_CUDA(ctx, up(o_c, g.c, used));
-    if (vec > used) {
-        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_a + used, 0, vec - used, st));
-        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_b + used, 0, vec - used, st));
-        B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_c + used, 0, vec - used, st));
+    for (uint32_t k = 0; k < K; k++) {
+        const ProveArgs &p = args[k];
+        B200ZK_CUDA(ctx, up(o_a + k * vec, p.a, used));
+        B200ZK_CUDA(ctx, up(o_b + k * vec, p.b, used));
+        B200ZK_CUDA(ctx, up(o_c + k * vec, p.c, used));
+        if (vec > used) {
+            B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_a + k * vec + used, 0, vec - used, st));
+            B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_b + k * vec + used, 0, vec - used, st));
+            B200ZK_CUDA(ctx, cudaMemsetAsync(w + o_c + k * vec + used, 0, vec - used, st));
+        }
     }
     trace.mark("a, b, c uploaded", st);
-    // ---- H polynomial (prover.rs:256-287)
-    if ((rc = ntt_h_poly(ctx, w + o_a, w + o_b, w + o_c, log_m, w + o_h))) return rc;
+    // ---- H polynomials (prover.rs:256-287)
+    for (uint32_t k = 0; k < K; k++)
+        if ((rc = ntt_h_poly(ctx, w + o_a + k * vec, w + o_b + k * vec, w + o_c + k * vec, log_m, w + o_h + k * vec))) return rc;
     trace.mark("h polynomial", st);
-    // ---- the 8 multiexps (prover.rs:289-318)
-    g1_jac_t *r1 = (g1_jac_t *)(w + o_r1);
-    g2_jac_t *r2 = (g2_jac_t *)(w + o_r2);
+    // ---- the multiexps (prover.rs:289-318), each over the whole batch
     uint32_t *stw = (uint32_t *)(w + o_st);
     const uint8_t *da = (const uint8_t *)(w + o_da), *db = (const uint8_t *)(w + o_db);
-    struct Job { const Bases *b; size_t off; size_t src; size_t n; const uint8_t *d; void *out; };
+    struct Job { const Bases *b; size_t src; size_t n; const uint8_t *d; size_t out; MsmBatch batch; };
     const int n_jobs = 5;
     Job jobs[n_jobs] = {
-        {crs->h, 0, o_h, m - 1, nullptr, &r1[R_H]},
-        {crs->l, 0, o_aux, g.n_aux, nullptr, &r1[R_L]},
-        {crs->a, 0, o_in, n_all, da, &r1[R_A]},
-        {crs->b_g1, 0, o_in, n_all, db, &r1[R_B1]},
-        {crs->b_g2, 0, o_in, n_all, db, &r2[R_B2]},
+        {crs->h, o_h, m - 1, nullptr, o_rh, {K, m, 0}},
+        {crs->l, o_in + g.n_inputs * 32, g.n_aux, nullptr, o_rl, {K, n_all, 0}},
+        {crs->a, o_in, n_all, da, o_ra, {K, n_all, n_all}},
+        {crs->b_g1, o_in, n_all, db, o_rb1, {K, n_all, n_all}},
+        {crs->b_g2, o_in, n_all, db, o_rb2, {K, n_all, n_all}},
     };
-    // The H multiexp needs the H polynomial; the other four only need the assignment, so they run beside it on the context's
-    // lanes (own stream and workspaces each) and join before the assembly.  B200ZK_PROVE_LANES=0 keeps everything on one stream.
+    // The H multiexp needs the H polynomials; the other four only need the assignments, so they run beside it on the context's
+    // lanes (own stream and workspaces each) and join before the last piece.  B200ZK_PROVE_LANES=0 keeps everything on one stream.
     int n_lanes = n_jobs - 1;
     if (const char *e = getenv("B200ZK_PROVE_LANES")) n_lanes = std::max(0, std::min(n_jobs - 1, atoi(e)));
     if (n_lanes && (rc = ctx_lanes(ctx, n_lanes))) return rc;
     const g1_affine_t *vk1 = (const g1_affine_t *)crs->vk;
     const g2_affine_t *vk2 = (const g2_affine_t *)((const char *)crs->vk + 3 * 96);
-    g1_jac_t *mid = (g1_jac_t *)(w + o_mid);  // sga, rb1
+    g1_jac_t *sga = (g1_jac_t *)(w + o_sga), *rb1 = (g1_jac_t *)(w + o_rb1r);
     uint8_t *dinf = (uint8_t *)(w + o_inf);
     const uint32_t *scal = (const uint32_t *)(w + o_scal);
     for (int j = 0; j < n_jobs; j++) {
@@ -223,15 +245,18 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
             B200ZK_CUDA(ctx, cudaStreamWaitEvent(on->stream, ctx->ev_fork, 0));
         }
         const unsigned long long before = on->launches;
-        if ((rc = msm_run(on, jobs[j].b, jobs[j].off, w + jobs[j].src, jobs[j].n, jobs[j].d, jobs[j].out, stw + j, 0)))
+        if ((rc = msm_run(on, jobs[j].b, 0, w + jobs[j].src, jobs[j].n, jobs[j].d, w + jobs[j].out, stw + (size_t)j * K, 0, jobs[j].batch)))
             return on == ctx ? rc : set_error(ctx, rc, on->last_error);
         static const char *const msm_names[] = {"multiexp H", "multiexp L", "multiexp A", "multiexp B-G1", "multiexp B-G2"};
         static const char *const piece_names[] = {"", "", "piece a (g_a, s*g_a)", "piece b1 (r*B1)", "piece b (g_b)"};
         trace.mark(msm_names[j], on->stream);
         // the piece of the assembly (prover.rs:326-363) that only needs this multiexp
-        if (j == 2) k_proof_a<<<1, 32, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, r1, mid, (g1_affine_t *)(w + o_pa), dinf);
-        if (j == 3) k_proof_b1<<<1, 32, 0, on->stream>>>(scal, vk1, r1, mid + 1);
-        if (j == 4) k_proof_b<<<1, 32, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, r2, (g2_affine_t *)(w + o_pb), dinf);
+        if (j == 2)
+            k_proof_a<<<K, 32, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, (const g1_jac_t *)(w + o_ra), sga, (g1_affine_t *)(w + o_pa), dinf);
+        if (j == 3) k_proof_b1<<<K, 32, 0, on->stream>>>(scal, vk1, (const g1_jac_t *)(w + o_rb1), rb1);
+        if (j == 4)
+            k_proof_b<<<K, 32, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, (const g2_jac_t *)(w + o_rb2),
+                                                                    (g2_affine_t *)(w + o_pb), dinf);
         if (j >= 2) { on->launches++; trace.mark(piece_names[j], on->stream); }
         if (on != ctx) ctx->launches += on->launches - before;
     }
@@ -240,25 +265,33 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_
         B200ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->lanes[l]->ev_join, 0));
     }
     trace.mark("join", st);
-    k_proof_c<<<1, 32, 0, st>>>(mid, mid + 1, r1, (g1_affine_t *)(w + o_pc), dinf);
+    k_proof_c<<<K, 32, 0, st>>>(sga, rb1, (const g1_jac_t *)(w + o_rh), (const g1_jac_t *)(w + o_rl), (g1_affine_t *)(w + o_pc), dinf);
     ctx->launches++;
     trace.mark("piece c", st);
     B200ZK_CUDA(ctx, cudaGetLastError());
-    uint32_t status[8];
-    uint8_t inf3[4];
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_a, w + o_pa, 96, cudaMemcpyDeviceToHost, st));
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_b, w + o_pb, 192, cudaMemcpyDeviceToHost, st));
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_c, w + o_pc, 96, cudaMemcpyDeviceToHost, st));
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(inf3, dinf, 3, cudaMemcpyDeviceToHost, st));
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(status, stw, sizeof(status), cudaMemcpyDeviceToHost, st));
+    std::vector<uint32_t> status(5 * (size_t)K);
+    std::vector<uint8_t> inf(4 * (size_t)K);
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_a, w + o_pa, K * 96, cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_b, w + o_pb, K * 192, cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(proof_c, w + o_pc, K * 96, cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(inf.data(), dinf, inf.size(), cudaMemcpyDeviceToHost, st));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(status.data(), stw, status.size() * 4, cudaMemcpyDeviceToHost, st));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
     trace.report();
-    for (int j = 0; j < n_jobs; j++) {
-        if (status[j] == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status[j], "UnexpectedIdentity in multiexp");
-        if (status[j] == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status[j], "IoError(UnexpectedEof) in multiexp");
+    for (uint32_t k = 0; k < K; k++) {
+        for (int j = 0; j < n_jobs; j++) {
+            const uint32_t code = status[(size_t)j * K + k];
+            const std::string which = K > 1 ? " (proof " + std::to_string(k) + " of the batch)" : "";
+            if (code == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, code, "UnexpectedIdentity in multiexp" + which);
+            if (code == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, code, "IoError(UnexpectedEof) in multiexp" + which);
+        }
+        if (inf_flags) { inf_flags[3 * k] = inf[4 * k]; inf_flags[3 * k + 1] = inf[4 * k + 1]; inf_flags[3 * k + 2] = inf[4 * k + 2]; }
     }
-    if (inf_flags) { inf_flags[0] = inf3[0]; inf_flags[1] = inf3[1]; inf_flags[2] = inf3[2]; }
     return B200ZK_OK;
+}
+
+int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &g, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c, uint8_t *inf_flags) {
+    return groth16_prove_batch(ctx, crs, &g, 1, proof_a, proof_b, proof_c, inf_flags);
 }
 
 }  // namespace b200zk

@@ -99,8 +99,15 @@ int ntt_divide_by_z_on_coset(Ctx *ctx, void *d_coeffs, uint32_t log_n);
 int ntt_domain_z(Ctx *ctx, const void *d_tau, uint32_t log_n, void *d_out);
 int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *d_out_repr);
 // msm.cu
+// A batch of K multiexps over the SAME bases (K proofs over one CRS): exponent vector k starts k * scalar_stride exponents
+// after the first, its density map k * density_stride bytes after the first; the K multiexps are separate bucket sets of one
+// pipeline, so small multiexps fill the machine together.  Results: K consecutive Jacobian points and K consecutive status words.
+struct MsmBatch {
+    uint32_t K = 1;
+    size_t scalar_stride = 0, density_stride = 0;
+};
 int msm_run(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density,
-            void *d_out_jac, void *d_status_out, int window_bits);
+            void *d_out_jac, void *d_status_out, int window_bits, MsmBatch batch = MsmBatch());
 int msm_fixed_base(Ctx *ctx, int group, const void *d_base_affine, const void *d_scalars, size_t n, uint32_t scalar_bits, void *d_out_affine,
                    uint8_t *d_out_inf);
 int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf);
@@ -128,5 +135,8 @@ struct ProveArgs {
     const uint64_t *r, *s;
 };
 int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &args, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c, uint8_t *inf_flags);
+// K proofs of one circuit in lock-step; outputs are K consecutive proofs (12 / 24 / 12 words, 3 flags each)
+int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_t K, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c,
+                        uint8_t *inf_flags);
 
 }  // namespace b200zk

@@ -4,7 +4,7 @@
 namespace b200zk {
 
 #define DECL(SUFFIX)                                                                                                                 \
-    int msm_run_##SUFFIX(Ctx *, const Bases *, size_t, const void *, size_t, const uint8_t *, void *, void *, int);                  \
+    int msm_run_##SUFFIX(Ctx *, const Bases *, size_t, const void *, size_t, const uint8_t *, void *, void *, int, MsmBatch);        \
     int msm_fixed_base_##SUFFIX(Ctx *, const void *, const void *, size_t, uint32_t, void *, uint8_t *);                             \
     int msm_into_affine_##SUFFIX(Ctx *, const void *, size_t, void *, uint8_t *);                                                    \
     int msm_sum_points_##SUFFIX(Ctx *, const void *, size_t, void *);                                                                \
@@ -14,9 +14,9 @@ DECL(g1)
 DECL(g2)
 
 int msm_run(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density, void *d_out_jac,
-            void *d_status_out, int window_bits) {
-    if (bases->group == B200ZK_G1) return msm_run_g1(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits);
-    return msm_run_g2(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits);
+            void *d_status_out, int window_bits, MsmBatch batch) {
+    if (bases->group == B200ZK_G1) return msm_run_g1(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits, batch);
+    return msm_run_g2(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits, batch);
 }
 int msm_fixed_base(Ctx *ctx, int group, const void *d_base_affine, const void *d_scalars, size_t n, uint32_t scalar_bits, void *d_out_affine,
                    uint8_t *d_out_inf) {

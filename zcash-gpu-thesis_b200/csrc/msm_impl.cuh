@@ -117,7 +117,9 @@ static int scan_u32(cudaStream_t st, const T *in, size_t n, uint32_t *out, uint3
 struct MsmShape {
     uint32_t c, W, B;  // window bits, windows (c*W >= 256), buckets per window = 2^(c-1)
     uint32_t pre_n;    // 0, or the stride of the precomputed base table (then all windows share one bucket set)
+    uint32_t sets;     // bucket sets per multiexp: 1 with the precomputed table, W without
 };
+static constexpr uint32_t ST_PER_K = 8;  // offset of the per-multiexp status triples inside the status area
 
 __device__ __forceinline__ uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
     uint32_t limb = pos >> 5, sh = pos & 31;
@@ -131,18 +133,21 @@ __device__ __forceinline__ uint32_t extract_bits(const uint32_t *s, uint32_t pos
 template <int MODE>
 __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__ scalars, size_t n_exp, const uint8_t *__restrict__ density,
                                                    const uint32_t *__restrict__ rank, size_t base_offset, size_t n_bases,
-                                                   const uint8_t *__restrict__ base_inf, MsmShape sh, uint32_t *__restrict__ counts_or_cursor,
-                                                   uint32_t *__restrict__ sorted, uint32_t *__restrict__ status) {
+                                                   const uint8_t *__restrict__ base_inf, MsmShape sh, MsmBatch batch,
+                                                   uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted,
+                                                   uint32_t *__restrict__ status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_exp) return;
-    if (density && !density[i]) return;  // no base consumed (multiexp.rs:175)
-    size_t idx = base_offset + (rank ? rank[i] : i);
+    const uint32_t k = blockIdx.y;  // which multiexp of the batch
+    status += ST_PER_K + 3 * k;
+    if (density && !density[k * batch.density_stride + i]) return;  // no base consumed (multiexp.rs:175)
+    size_t idx = base_offset + (rank ? rank[k * (n_exp + 1) + i] : i);
     if (idx >= n_bases) {  // Source::{skip, add_assign_mixed} both fail first on an exhausted source (multiexp.rs:44, 60)
         if (MODE == 0) atomicMin(&status[0], (uint32_t)i);
         return;
     }
     uint32_t s[8];
-    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + 8 * i);
+    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + 8 * (k * batch.scalar_stride + i));
     uint4 lo = sp[0], hi = sp[1];
     s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
     if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;  // exp == zero: skip(1)
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
         carry = neg;
         if (d == 0) continue;
         // with precomputed 2^(c w) * P the digit of window w is a digit of window 0 for the point w * n + idx
-        uint32_t slot = (sh.pre_n ? 0u : w * sh.B) + d - 1;
+        uint32_t slot = (k * sh.sets + (sh.pre_n ? 0u : w)) * sh.B + d - 1;
         if (MODE == 0) {
             atomicAdd(&counts_or_cursor[slot], 1u);
         } else {
@@ -367,27 +372,32 @@ __global__ void k_msm_slice_final(const XYZZ<F> *__restrict__ Y, uint32_t nb, ui
 template <class F>
 __global__ void k_msm_window_combine(const XYZZ<F> *__restrict__ R, const XYZZ<F> *__restrict__ A, MsmShape sh, Jacobian<F> *__restrict__ out,
                                      uint32_t *__restrict__ status, uint32_t *__restrict__ status_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x != 0) return;
+    const uint32_t k = blockIdx.x;  // multiexp of the batch: its bucket sets are [k * sets, (k + 1) * sets)
+    R += (size_t)k * sh.sets;
+    A += (size_t)k * sh.sets;
     XYZZ<F> acc = XYZZ<F>::zero();
-    for (uint32_t w = sh.W; w-- > 0;) {
+    for (uint32_t w = sh.sets; w-- > 0;) {
         for (uint32_t d = 0; d < sh.c; d++) acc.dbl();
         XYZZ<F> t = A[w];
         t.add(R[w]);
         acc.add(t);
     }
-    *out = acc.to_jacobian();
+    out[k] = acc.to_jacobian();
+    status += ST_PER_K + 3 * k;
     uint32_t eof = status[0], ident = status[1];
     uint32_t st = B200ZK_OK;
     if (eof != NO_POS || ident != NO_POS) st = eof < ident ? B200ZK_ERR_UNEXPECTED_EOF : B200ZK_ERR_UNEXPECTED_IDENTITY;
     status[2] = st;
-    if (status_out) *status_out = st;
+    if (status_out) status_out[k] = st;
 }
 
 template <class F>
 __global__ void k_write_zero_point(Jacobian<F> *out, uint32_t *status, uint32_t *status_out) {
-    *out = Jacobian<F>::zero();
-    status[2] = 0;
-    if (status_out) *status_out = 0;
+    const uint32_t k = blockIdx.x;
+    out[k] = Jacobian<F>::zero();
+    status[ST_PER_K + 3 * k + 2] = 0;
+    if (status_out) status_out[k] = 0;
 }
 
 static uint32_t msm_default_window(size_t n) {
@@ -407,9 +417,11 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 template <class F>
 static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density,
-                     void *d_out_jac, void *d_status_out, int window_bits) {
+                     void *d_out_jac, void *d_status_out, int window_bits, MsmBatch batch) {
     cudaStream_t st = ctx->stream;
     if (n_exp >= (1ull << 31) || bases->n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "n >= 2^31 not supported");
+    if (batch.K == 0 || batch.K > 4096) return set_error(ctx, B200ZK_ERR_BAD_ARG, "batch must be in [1, 4096]");
+    const uint32_t K = batch.K;
     MsmShape sh;
     const bool use_pre = bases->pre != nullptr && (window_bits <= 0 || (uint32_t)window_bits == bases->pre_c);
     sh.c = use_pre ? bases->pre_c : window_bits > 0 ? (uint32_t)window_bits : msm_default_window(n_exp);
@@ -417,24 +429,26 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     sh.W = (256 + sh.c - 1) / sh.c;
     sh.B = 1u << (sh.c - 1);
     sh.pre_n = use_pre ? (uint32_t)bases->n : 0u;
-    const uint32_t bw = use_pre ? 1u : sh.W;  // bucket sets
+    sh.sets = use_pre ? 1u : sh.W;
+    const uint32_t bw = K * sh.sets;  // bucket sets of the whole batch
     const size_t nbk = (size_t)bw * sh.B;
-    if (nbk + n_exp * sh.W >= (1ull << 32)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "n * windows >= 2^32 not supported");
+    const size_t refs_max = (size_t)K * n_exp * sh.W;  // digits of the whole batch
+    if (nbk + refs_max >= (1ull << 32)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "batch * n * windows >= 2^32 not supported");
     const void *point_table = use_pre ? bases->pre : bases->points;
 
     // workspace carve-up
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    size_t o_status = take(8 * sizeof(uint32_t));
+    size_t o_status = take((ST_PER_K + 3 * (size_t)K) * sizeof(uint32_t));
     size_t o_counts = take((nbk + 1) * sizeof(uint32_t));
     size_t o_offsets = take((nbk + 1) * sizeof(uint32_t));
     size_t o_cursor = take((nbk + 1) * sizeof(uint32_t));
     size_t o_sums = take((std::max(nbk, n_exp) / SCAN_BLOCK + 2) * sizeof(uint32_t));
-    size_t o_rank = take(d_density ? (n_exp + 1) * sizeof(uint32_t) : 0);
-    size_t o_sorted = take(n_exp * sh.W * sizeof(uint32_t));
+    size_t o_rank = take(d_density ? K * (n_exp + 1) * sizeof(uint32_t) : 0);
+    size_t o_sorted = take(refs_max * sizeof(uint32_t));
     size_t o_buckets = take(nbk * sizeof(XYZZ<F>));
     // bucket splitting: cap = 2 x mean bucket load + 32; at most n*W/cap + nbk... split tasks, bounded by 2*n*W/cap
-    const size_t mean_load = n_exp * (sh.W / bw) / sh.B;
+    const size_t mean_load = n_exp * (sh.W / sh.sets) / sh.B;
     uint32_t cap = (uint32_t)(mean_load + mean_load / 2 + 32);  // chains longer than ~1.5 x the mean are split
     {
         // A small multiexp cannot fill the machine with one thread per bucket: its time is (longest chain) x (latency of one
@@ -443,11 +457,11 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
         const size_t slots = (size_t)ctx->sm_count * (sizeof(F) > 48 ? B200ZK_ACC_MINBLOCKS_G2 : B200ZK_ACC_MINBLOCKS) * 128;
         if (waves > 0) {
-            const size_t fill = (size_t)((double)(n_exp * sh.W) / (waves * (double)slots));
+            const size_t fill = (size_t)((double)refs_max / (waves * (double)slots));
             cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(8, fill));
         }
     }
-    const size_t max_tasks = (size_t)2 * n_exp * sh.W / cap + 2;
+    const size_t max_tasks = (size_t)2 * refs_max / cap + 2;
     size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
     size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
     size_t o_shist = take((cap + 2) * sizeof(uint32_t)), o_scur = take((cap + 2) * sizeof(uint32_t)), o_order = take((nbk + 1) * sizeof(uint32_t));
@@ -464,7 +478,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     // points are bound by dependent gathers, not by the multiplier pipe.  Opt-in only.
     bool use_ba = false;
     if (const char *e = getenv("B200ZK_BA")) use_ba = e[0] == '1';
-    const size_t refs_bound = n_exp * sh.W;
+    const size_t refs_bound = refs_max;
     size_t o_ba = use_ba ? take(ba_workspace_bytes<F>(nbk, refs_bound)) : 0;
     int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, off);
     if (rc) return rc;
@@ -478,20 +492,22 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     uint32_t *size_hist = (uint32_t *)(ws + o_shist), *size_cur = (uint32_t *)(ws + o_scur), *order = (uint32_t *)(ws + o_order);
     XYZZ<F> *lr[2] = {(XYZZ<F> *)(ws + o_r0), (XYZZ<F> *)(ws + o_r1)}, *la[2] = {(XYZZ<F> *)(ws + o_a0), (XYZZ<F> *)(ws + o_a1)};
 
-    B200ZK_CUDA(ctx, cudaMemsetAsync(status, 0xff, 2 * sizeof(uint32_t), st));
+    B200ZK_CUDA(ctx, cudaMemsetAsync(status + ST_PER_K, 0xff, 3 * (size_t)K * sizeof(uint32_t), st));
     if (n_exp == 0) {
-        k_write_zero_point<F><<<1, 1, 0, st>>>((Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
+        k_write_zero_point<F><<<K, 1, 0, st>>>((Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
         B200ZK_CUDA(ctx, cudaGetLastError());
         return B200ZK_OK;
     }
     B200ZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (nbk + 1) * sizeof(uint32_t), st));
-    if (d_density) ctx->launches += scan_u32<uint8_t>(st, d_density, n_exp, rank, nullptr, sums);
-    const unsigned eb = (unsigned)((n_exp + 255) / 256);
-    k_msm_digits<0><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, counts,
-                                        nullptr, status);
+    if (d_density)
+        for (uint32_t k = 0; k < K; k++)
+            ctx->launches += scan_u32<uint8_t>(st, d_density + k * batch.density_stride, n_exp, rank + k * (n_exp + 1), nullptr, sums);
+    const dim3 eb((unsigned)((n_exp + 255) / 256), K);
+    k_msm_digits<0><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, batch,
+                                        counts, nullptr, status);
     ctx->launches += scan_u32<uint32_t>(st, counts, nbk, offsets, cursor, sums);
-    k_msm_digits<1><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, cursor,
-                                        sorted, status);
+    k_msm_digits<1><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, batch,
+                                        cursor, sorted, status);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->prof_on) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
     if (use_ba) {
@@ -556,9 +572,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         ctx->launches++;
         inR = lr[pp]; inA = la[pp];
     }
-    MsmShape comb = sh;
-    comb.W = bw;
-    k_msm_window_combine<F><<<1, 1, 0, st>>>(inR, inA, comb, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
+    k_msm_window_combine<F><<<K, 1, 0, st>>>(inR, inA, sh, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
@@ -701,8 +715,8 @@ static int msm_sum_points_t(Ctx *ctx, const void *d_jac_in, size_t n, void *d_ja
 // one translation unit per group (msm_g1.cu / msm_g2.cu) instantiates these for its coordinate field
 #define B200ZK_MSM_INSTANTIATE(SUFFIX, F)                                                                                          \
     int msm_run_##SUFFIX(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scalars, size_t n_exp, const uint8_t *d_density, \
-                         void *d_out_jac, void *d_status_out, int window_bits) {                                                   \
-        return msm_run_t<F>(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits);           \
+                         void *d_out_jac, void *d_status_out, int window_bits, MsmBatch batch) {                                   \
+        return msm_run_t<F>(ctx, bases, base_offset, d_scalars, n_exp, d_density, d_out_jac, d_status_out, window_bits, batch);    \
     }                                                                                                                              \
     int msm_fixed_base_##SUFFIX(Ctx *ctx, const void *d_base, const void *d_scalars, size_t n, uint32_t bits, void *d_out, uint8_t *d_out_inf) { \
         return msm_fixed_base_t<F>(ctx, d_base, d_scalars, n, bits, d_out, d_out_inf);                                             \
