@@ -79,6 +79,7 @@ int b200zk_dev_alloc(b200zk_ctx *ctx, size_t bytes, void **dptr);
 int b200zk_dev_free(b200zk_ctx *ctx, void *dptr);
 int b200zk_h2d(b200zk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int b200zk_d2h(b200zk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int b200zk_d2d(b200zk_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes); /* stream-ordered device copy */
 int b200zk_host_alloc_pinned(size_t bytes, void **hptr);
 int b200zk_host_free_pinned(void *hptr);
 int b200zk_timer_start(b200zk_ctx *ctx);            /* cudaEventRecord on the context's stream */
@@ -184,6 +185,10 @@ int b200zk_divide_by_z_on_coset_dev(b200zk_ctx *ctx, void *d_coeffs, uint32_t lo
 int b200zk_domain_z(b200zk_ctx *ctx, const uint64_t tau[4], uint32_t log_m, uint64_t out[4]);
 /* coeffs[i] *= s (ifft's m^-1 scaling; domain.rs:88-103) */
 int b200zk_fr_scale_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_t s[4]);
+/* y[v] = sum over k in [row_ptr[v], row_ptr[v+1]) of val[k] * x[col[k]]  (Fr, Montgomery; u32 CSR indices; device memory,
+ * stream-ordered).  The numeric core of generate_parameters' eval (generator.rs:301-414): row v = the (coeff, constraint)
+ * terms of variable v in A, B or C, x = the Lagrange coefficients L_i(tau) (powers of tau after ifft, generator.rs:292). */
+int b200zk_fr_spmv_dev(b200zk_ctx *ctx, const void *d_row_ptr, const void *d_col, const void *d_val, const void *d_x, size_t n_rows, void *d_y);
 /* point ops on host arrays (parity tests): a = Jacobian points; b = Jacobian (ADD) or affine x||y (ADD_MIXED) */
 int b200zk_point_op(b200zk_ctx *ctx, int group, int op, const uint64_t *a, const uint64_t *b, const uint8_t *b_inf, uint64_t *out, size_t n);
 

@@ -36,4 +36,5 @@ from .bellman import (  # noqa: F401
     ntt_host,
     point_op,
 )
+from .generator import GeneratedParameters, KeypairAssembly, UnconstrainedVariable, generate_parameters  # noqa: F401
 from ._lib import G1, G2, FR, FQ, FFT, IFFT, COSET_FFT, ICOSET_FFT  # noqa: F401

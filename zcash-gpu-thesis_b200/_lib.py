@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200zk_dev_free": (_i, [_vp, _vp]),
     "b200zk_h2d": (_i, [_vp, _vp, _vp, _sz]),
     "b200zk_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "b200zk_d2d": (_i, [_vp, _vp, _vp, _sz]),
     "b200zk_host_alloc_pinned": (_i, [_sz, C.POINTER(_vp)]),
     "b200zk_host_free_pinned": (_i, [_vp]),
     "b200zk_timer_start": (_i, [_vp]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "b200zk_ntt": (_i, [_vp, _vp, _u32, _i]),
     "b200zk_ntt_dev": (_i, [_vp, _vp, _u32, _i]),
     "b200zk_distribute_powers_dev": (_i, [_vp, _vp, _sz, _vp]),
+    "b200zk_fr_spmv_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200zk_field_vec_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     "b200zk_field_vec": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     "b200zk_divide_by_z_on_coset_dev": (_i, [_vp, _vp, _u32]),

@@ -182,6 +182,12 @@ int b200zk_h2d(b200zk_ctx *ctx, void *dst_dev, const void *src_host, size_t byte
     B200ZK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return B200ZK_OK;
 }
+int b200zk_d2d(b200zk_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes) {
+    CHECK_CTX(ctx);
+    USE_DEVICE(ctx);
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200ZK_OK;
+}
 int b200zk_d2h(b200zk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
     CHECK_CTX(ctx);
     USE_DEVICE(ctx);
@@ -644,6 +650,13 @@ int b200zk_fr_scale_dev(b200zk_ctx *ctx, void *d_coeffs, size_t n, const uint64_
     if (rc) return rc;
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
+}
+
+int b200zk_fr_spmv_dev(b200zk_ctx *ctx, const void *d_row_ptr, const void *d_col, const void *d_val, const void *d_x, size_t n_rows, void *d_y) {
+    CHECK_CTX(ctx);
+    if (n_rows && (!d_row_ptr || !d_y)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    USE_DEVICE(ctx);
+    return launch_fr_spmv(ctx, d_row_ptr, d_col, d_val, d_x, n_rows, d_y);
 }
 
 int b200zk_field_vec_dev(b200zk_ctx *ctx, int field, int op, const void *d_a, const void *d_b, void *d_out, size_t n) {

@@ -2,6 +2,8 @@
 // (bellman/src/bls12-381.cl:799-887 test_fq_*, :1612-1700 test_fr_*, :1045-1170 test_projective_*), of
 // EvaluationDomain::{mul_assign, sub_assign} and the scaling loops (bellman/src/domain.rs:88-103, 146-189),
 // plus the integer-pipe calibration micro-benchmarks.
+#include <algorithm>
+
 #include "ec.cuh"
 #include "internal.h"
 
@@ -49,6 +51,34 @@ __global__ void k_fr_scale(fr_t *__restrict__ a, const fr_t *__restrict__ s, siz
 int launch_fr_scale(Ctx *ctx, void *a, const void *scalar_dev, size_t n) {
     if (n == 0) return B200ZK_OK;
     k_fr_scale<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((fr_t *)a, (const fr_t *)scalar_dev, n);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// ---- y = M x over Fr, M in CSR form: the evaluation of the QAP polynomials at tau in generate_parameters
+// (generator.rs:361-380 eval_at_tau: sum over the (coeff, constraint index) terms of one variable of coeff * L_index(tau)).
+// One warp per row: rows are short except the one of the constant ONE, which touches most constraints.
+__global__ void __launch_bounds__(128) k_fr_spmv(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, const fr_t *__restrict__ val,
+                                                const fr_t *__restrict__ x, size_t n_rows, fr_t *__restrict__ y) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+        fr_t acc = fr_t::zero();
+        for (uint32_t k = row_ptr[row] + lane; k < row_ptr[row + 1]; k += 32) acc = acc + val[k] * x[col[k]];
+        for (uint32_t off = 16; off > 0; off >>= 1) {
+            fr_t other;
+#pragma unroll
+            for (int j = 0; j < 8; j++) other.v[j] = __shfl_down_sync(0xffffffffu, acc.v[j], off);
+            acc = acc + other;
+        }
+        if (lane == 0) y[row] = acc;
+    }
+}
+int launch_fr_spmv(Ctx *ctx, const void *row_ptr, const void *col, const void *val, const void *x, size_t n_rows, void *y) {
+    if (n_rows == 0) return B200ZK_OK;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_rows + 3) / 4, (size_t)ctx->sm_count * 16);
+    k_fr_spmv<<<blocks, 128, 0, ctx->stream>>>((const uint32_t *)row_ptr, (const uint32_t *)col, (const fr_t *)val, (const fr_t *)x, n_rows, (fr_t *)y);
+    ctx->launches++;
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }

@@ -88,6 +88,7 @@ struct Bases {
 // field_kernels.cu
 int launch_field_vec(Ctx *ctx, int field, int op, const void *a, const void *b, void *out, size_t n);
 int launch_fr_scale(Ctx *ctx, void *a, const void *scalar_dev, size_t n);
+int launch_fr_spmv(Ctx *ctx, const void *row_ptr, const void *col, const void *val, const void *x, size_t n_rows, void *y);
 int launch_point_op(Ctx *ctx, int group, int op, const void *a, const void *b, const uint8_t *b_inf, void *out, size_t n);
 int launch_microbench(Ctx *ctx, int kind, int iters, int blocks, int threads, void *out);
 // ntt.cu
