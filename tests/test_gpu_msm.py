@@ -373,3 +373,48 @@ def test_batched_multiexp_reports_the_failing_member(worker):
     exps[2, 40] = 0
     with pytest.raises(zk.IoError, match="multiexp 0"):
         zk.multiexp_batch(worker, (bases, 50), None, exps)  # 60 exponents, 50 bases left
+
+
+@pytest.mark.parametrize("group,log_n", [("g1", 24), ("g2", 22)])
+def test_baseline_full_sizes_through_the_discrete_log_identity(worker, group, log_n):
+    """BASELINE.json configs 3 / 4 at their full sizes (G1 2^24, G2 2^22), far beyond what the CPU oracle finishes: bases are
+    [k_i]G made on the device, so sum s_i P_i must equal [sum s_i k_i]G; the plain-window schedule, the precomputed-table
+    schedule and the sum of two half-range shards (the multi-GPU decomposition) must all give that same point."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import zcash_gpu_thesis_b200 as zk
+
+    code = zk.G1 if group == "g1" else zk.G2
+    gen = util.g1_gen_limbs() if group == "g1" else bench.gen_g2_limbs()
+    n = 1 << log_n
+    r = np.random.default_rng(77 + log_n)
+    k = np.zeros((n, 4), dtype=np.uint64)
+    k[:, 0] = r.integers(1, 1 << 64, size=n, dtype=np.uint64)
+    dxy, dinf, _ = zk.fixed_base_mul(worker, code, gen, k, 64)
+    bases = zk.Bases.from_device(worker, code, dxy, n)
+    dxy.free(); dinf.free()
+    exps = bench.random_scalars(r, n)
+    exps[5] = 0
+    exps[6] = (1, 0, 0, 0)
+    exps[7] = int_to_limbs(Fr.p - 1, 4)
+    want_xy, want_inf = util.affine_of_scalar(group, bench.dot_mod_r(k[:, 0], exps))
+    assert not want_inf
+
+    def affine(jac):
+        aff, inf = zk.into_affine(worker, code, jac)
+        assert not inf[0]
+        return aff[0]
+
+    plain = zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)
+    assert np.array_equal(affine(plain), want_xy)
+    half = n // 2
+    lo = zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps[:half])
+    hi = zk.multiexp(worker, (bases, half), zk.FullDensity(), exps[half:])
+    both = zk.point_op(worker, code, zk._lib.POINT_ADD, lo.reshape(1, -1), hi.reshape(1, -1))
+    assert np.array_equal(affine(both[0]), want_xy)
+    bases.precompute(0)
+    assert np.array_equal(affine(zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)), want_xy)
+    bases.free()
