@@ -92,3 +92,30 @@ def test_from_coeffs_degree_check_is_host_side():
             exp += 1
             if exp >= zk.bellman.FR_S:
                 raise zk.PolynomialDegreeTooLarge()
+
+
+def test_product_synthesis_matches_the_oracle():
+    """ProvingAssignment / KeypairAssembly of the product (host logic, prover.rs:84-234, generator.rs:57-212) against the oracle's"""
+    import zcash_gpu_thesis_b200 as zk
+    from oracle.fields import Fr
+    from oracle.groth16 import KeypairAssembly as OracleAssembly
+    from oracle.groth16 import synthesize_assignment
+    from oracle.pairing import Bls12
+    from tests.test_gpu_groth16 import MiMCLike
+
+    consts = [(i * 7919 + 3) ** 5 % Fr.p for i in range(9)]
+    circ = MiMCLike(12345, Fr.p - 5, consts)
+    want = synthesize_assignment(Bls12, circ)
+    got = zk.synthesize(circ)
+    assert got.a == want.a and got.b == want.b and got.c == want.c
+    assert got.input_assignment == want.input_assignment and got.aux_assignment == want.aux_assignment
+    assert [bool(x) for x in got.a_aux_density] == want.a_aux_density and [bool(x) for x in got.b_aux_density] == want.b_aux_density
+    assert [bool(x) for x in got.b_input_density] == want.b_input_density
+    a, b, c, inputs, aux, da, dbi, dba, r, s = got.as_tuple(Fr.p + 3, 9)
+    assert a.shape == (len(want.a), 4) and inputs.shape == (len(want.input_assignment), 4) and da.dtype.name == "uint8" and r == 3
+    assert list(map(int, a[1])) == Fr.to_mont_limbs(want.a[1])
+    asm, oasm = zk.KeypairAssembly(), OracleAssembly(Fr)
+    for x in (asm, oasm):
+        x.alloc_input()
+        circ.synthesize(x)
+    assert asm.at_aux == oasm.at_aux and asm.bt_aux == oasm.bt_aux and asm.ct_inputs == oasm.ct_inputs and asm.num_constraints == oasm.num_constraints

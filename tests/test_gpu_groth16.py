@@ -147,6 +147,32 @@ def test_batched_proofs_equal_single_proofs(worker):
         zk.create_proofs_from_assignments(worker, dev, [batch[0], tuple(x[:-1] for x in batch[1][:3]) + batch[1][3:]])  # fewer constraints
 
 
+def test_circuit_facing_api(worker):
+    """create_proof / create_random_proof / create_proofs (prover.rs:192-211): synthesis by the product's own
+    ProvingAssignment, then the GPU prover; fixed (r, s) gives the oracle's bytes, random (r, s) verifies."""
+    import random
+
+    import zcash_gpu_thesis_b200 as zk
+
+    E = BlsEngine
+    r0 = util.rng(2200)
+    rnd = lambda: util.rows_to_ints(util.random_fr_repr(r0, 1))[0]
+    consts = [rnd() for _ in range(12)]
+    params, _ = generate_parameters(E, MiMCLike(0, 0, consts), G1.gen, G2.gen, *[rnd() for _ in range(5)])
+    dev = _upload(worker, params)
+    circ = MiMCLike(rnd(), rnd(), consts)
+    r, s = rnd(), rnd()
+    asg = synthesize_assignment(E, circ)
+    assert zk.create_proof(worker, circ, dev, r, s).write(worker) == proof_bytes(prove_from_assignment(E, asg, params, r, s))
+    aff = lambda G, limbs: tuple([G.F.from_mont_limbs(list(map(int, limbs[: len(limbs) // 2]))), G.F.from_mont_limbs(list(map(int, limbs[len(limbs) // 2:]))), False])
+    p = zk.create_random_proof(worker, circ, dev, random.Random(7))
+    assert verify_proof(E, params.vk, OracleProof(a=aff(G1, p.a), b=aff(G2, p.b), c=aff(G1, p.c)), asg.input_assignment[1:])
+    circs = [MiMCLike(rnd(), rnd(), consts) for _ in range(3)]
+    rs = [(rnd(), rnd()) for _ in range(3)]
+    for c, (ri, si), got in zip(circs, rs, zk.create_proofs(worker, circs, dev, rs)):
+        assert got.write(worker) == proof_bytes(prove_from_assignment(E, synthesize_assignment(E, c), params, ri, si))
+
+
 def test_subversion_check(worker):
     """prover.rs:320-324: delta at infinity -> UnexpectedIdentity."""
     import zcash_gpu_thesis_b200 as zk

@@ -24,6 +24,12 @@ from .bellman import (  # noqa: F401
     Worker,
     create_proof_from_assignment,
     create_proofs_from_assignments,
+    create_proof,
+    create_random_proof,
+    create_proofs,
+    ProvingAssignment,
+    synthesize,
+    ONE,
     decode_points,
     encode_points,
     field_vec,

@@ -719,3 +719,80 @@ def create_proofs_from_assignments(worker, params: Parameters, assignments, lock
     if st:
         _raise(worker, st)
     return [Proof(pa[i], pb[i], pc[i], inf[i]) for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------- circuit-facing prover API
+ONE = ("in", 0)  # ConstraintSystem::one() (bellman/src/lib.rs): the first input variable
+
+
+class ProvingAssignment:
+    """prover.rs:84-190: the ConstraintSystem a circuit is synthesized into by create_proof.  Collects the a / b / c evaluation
+    vectors, the input / aux assignments and the three density trackers; host arithmetic (Python ints mod r), as in the
+    reference synthesis is CPU work.  Variables are ("in", i) / ("aux", i); a linear combination is [(variable, coeff), ...]."""
+
+    def __init__(self):
+        self.a, self.b, self.c = [], [], []
+        self.input_assignment, self.aux_assignment = [], []
+        self.a_aux_density, self.b_input_density, self.b_aux_density = [], [], []
+
+    def alloc(self, f):
+        self.aux_assignment.append(f() % FR_MODULUS)
+        self.a_aux_density.append(0)
+        self.b_aux_density.append(0)
+        return ("aux", len(self.aux_assignment) - 1)
+
+    def alloc_input(self, f):
+        self.input_assignment.append(f() % FR_MODULUS)
+        self.b_input_density.append(0)
+        return ("in", len(self.input_assignment) - 1)
+
+    def _eval(self, lc, input_density, aux_density):  # prover.rs:45-82
+        acc = 0
+        for (kind, i), coeff in lc:
+            if kind == "in":
+                v = self.input_assignment[i]
+                if input_density is not None:
+                    input_density[i] = 1
+            else:
+                v = self.aux_assignment[i]
+                if aux_density is not None:
+                    aux_density[i] = 1
+            acc += v * (coeff % FR_MODULUS)
+        return acc % FR_MODULUS
+
+    def enforce(self, a, b, c):  # prover.rs:153-186
+        self.a.append(self._eval(a, None, self.a_aux_density))  # inputs have full density in the A query (prover.rs:161-166)
+        self.b.append(self._eval(b, self.b_input_density, self.b_aux_density))
+        self.c.append(self._eval(c, None, None))
+
+    def as_tuple(self, r, s):
+        mont = lambda v: np.array([fr_to_mont_limbs(x) for x in v], dtype=np.uint64).reshape(len(v), 4)
+        rep = lambda v: np.array([[(x >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for x in v], dtype=np.uint64).reshape(len(v), 4)
+        u8 = lambda v: np.array(v, dtype=np.uint8)
+        return (mont(self.a), mont(self.b), mont(self.c), rep(self.input_assignment), rep(self.aux_assignment), u8(self.a_aux_density),
+                u8(self.b_input_density), u8(self.b_aux_density), r % FR_MODULUS, s % FR_MODULUS)
+
+
+def synthesize(circuit) -> ProvingAssignment:
+    """prover.rs:212-234: allocate ONE, synthesize the circuit, add the `input * 0 = 0` rows"""
+    prover = ProvingAssignment()
+    prover.alloc_input(lambda: 1)
+    circuit.synthesize(prover)
+    for i in range(len(prover.input_assignment)):
+        prover.enforce([(("in", i), 1)], [], [])
+    return prover
+
+
+def create_proof(worker, circuit, params: Parameters, r: int, s: int) -> Proof:
+    """groth16::create_proof (prover.rs:205-364): synthesis on the host, everything else in b200zk_groth16_prove"""
+    return create_proof_from_assignment(worker, params, *synthesize(circuit).as_tuple(r, s))
+
+
+def create_random_proof(worker, circuit, params: Parameters, rng) -> Proof:
+    """groth16::create_random_proof (prover.rs:192-203): r, s <- rng (`rng.randrange(n)` like random.Random / SystemRandom)"""
+    return create_proof(worker, circuit, params, rng.randrange(FR_MODULUS), rng.randrange(FR_MODULUS))
+
+
+def create_proofs(worker, circuits, params: Parameters, rs, lockstep=0):
+    """A run of create_proof calls over one CRS and one circuit shape, proved in lock-step groups (b200zk_groth16_prove_batch)"""
+    return create_proofs_from_assignments(worker, params, [synthesize(c).as_tuple(r, s) for c, (r, s) in zip(circuits, rs)], lockstep)
