@@ -10,6 +10,7 @@
 //
 // Header only; every arithmetic operation happens on the GPU inside libb200zk.so (there is no CPU fallback).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -212,6 +213,37 @@ inline Proof create_proof(const Worker &w, const Parameters &params, const Provi
                                  p.input_assignment.size(), p.aux_assignment.empty() ? nullptr : p.aux_assignment[0].data(), p.aux_assignment.size(),
                                  p.a_aux_density.bv.data(), p.b_input_density.bv.data(), p.b_aux_density.bv.data(), r.data(), s.data(), out.a.data(),
                                  out.b.data(), out.c.data(), out.infinity.data()));
+    return out;
+}
+
+// A run of create_proof calls over one CRS and one circuit (the spend proofs of one transaction, rustzcash.rs:1375): proved
+// `lockstep` at a time by b200zk_groth16_prove_batch (0 = the library default of 8).  rs[i] = (r, s) of proof i.
+inline std::vector<Proof> create_proofs(const Worker &w, const Parameters &params, const std::vector<const ProvingAssignment *> &ps,
+                                        const std::vector<std::pair<FrRepr, FrRepr>> &rs, int lockstep = 0) {
+    const size_t n = ps.size();
+    std::vector<Proof> out(n);
+    if (n == 0) return out;
+    if (rs.size() != n) throw std::invalid_argument("one (r, s) pair per proof");
+    std::vector<b200zk_prove_input> rows(n);
+    for (size_t i = 0; i < n; i++) {
+        const ProvingAssignment &p = *ps[i];
+        if (p.a.size() != ps[0]->a.size() || p.input_assignment.size() != ps[0]->input_assignment.size() ||
+            p.aux_assignment.size() != ps[0]->aux_assignment.size())
+            throw std::invalid_argument("the proofs of a batch must come from the same circuit");
+        rows[i] = b200zk_prove_input{p.a[0].data(), p.b[0].data(), p.c[0].data(), p.input_assignment[0].data(),
+                                     p.aux_assignment.empty() ? nullptr : p.aux_assignment[0].data(), p.a_aux_density.bv.data(),
+                                     p.b_input_density.bv.data(), p.b_aux_density.bv.data(), rs[i].first.data(), rs[i].second.data()};
+    }
+    std::vector<uint64_t> a(12 * n), b(24 * n), c(12 * n);
+    std::vector<uint8_t> inf(3 * n);
+    w.check(b200zk_groth16_prove_batch(w.ctx(), params.handle(), rows.data(), n, ps[0]->a.size(), ps[0]->input_assignment.size(),
+                                       ps[0]->aux_assignment.size(), lockstep, a.data(), b.data(), c.data(), inf.data()));
+    for (size_t i = 0; i < n; i++) {
+        std::copy_n(a.begin() + 12 * i, 12, out[i].a.begin());
+        std::copy_n(b.begin() + 24 * i, 24, out[i].b.begin());
+        std::copy_n(c.begin() + 12 * i, 12, out[i].c.begin());
+        std::copy_n(inf.begin() + 3 * i, 3, out[i].infinity.begin());
+    }
     return out;
 }
 
