@@ -20,8 +20,10 @@
  *     The representative is not unique; compare with the reference's PartialEq (ec.rs:45-85) or after
  *     into_affine.  Field / affine / NTT outputs are canonical and bit-identical to the reference.
  *   - No exceptions, no aborts: every call returns a status; b200zk_last_error() has the text.
- *   - One context = one GPU + one CUDA stream.  Calls on one context are stream-ordered; use one context per
- *     thread / in-flight future (the prover keeps 8 multiexps in flight, prover.rs:289-318).
+ *   - One context = one GPU + one CUDA stream.  Calls on one context are stream-ordered and thread-safe (each entry
+ *     holds the context's lock, so concurrent callers are serialised -- `Worker` is Clone in the reference and may be
+ *     shared); for concurrency use one context per thread, the _async futures (the prover keeps 8 multiexps in
+ *     flight, prover.rs:289-318) or the batch entry points.
  *   - There is NO CPU fallback: without a CUDA device every compute entry returns B200ZK_ERR_CUDA.
  */
 #ifndef B200ZK_H

@@ -418,3 +418,40 @@ def test_baseline_full_sizes_through_the_discrete_log_identity(worker, group, lo
     bases.precompute(0)
     assert np.array_equal(affine(zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)), want_xy)
     bases.free()
+
+
+def test_one_context_shared_by_several_threads(worker):
+    """`Worker` is Clone in the reference and multiexp may be called from any thread (multicore.rs:19-49): calls on one
+    context from concurrent host threads are serialised by the library and all give the right answer."""
+    import threading
+
+    import zcash_gpu_thesis_b200 as zk
+
+    r = util.rng(4300)
+    n = 3000
+    xy, _ = util.random_bases("g1", r, n)
+    bases = zk.Bases(worker, zk.G1, xy)
+    jobs = [util.random_fr_repr(r, n - 100 * t) for t in range(6)]
+    got, errs = [None] * len(jobs), []
+
+    def run(t):
+        try:
+            for _ in range(3):
+                got[t] = zk.multiexp(worker, (bases, t), zk.FullDensity(), jobs[t])
+                d = zk.EvaluationDomain.from_coeffs(worker, jobs[t][:256] >> np.uint64(2))
+                d.fft(worker)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=run, args=(t,)) for t in range(len(jobs))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for t, exps in enumerate(jobs):
+        st, want = cref.multiexp("g1", xy, exps, base_offset=t)
+        assert st == 0
+        got_aff, got_inf = zk.into_affine(worker, zk.G1, got[t])
+        want_aff, want_inf = cref.into_affine("g1", want)
+        assert bool(got_inf[0]) == want_inf and np.array_equal(got_aff[0], want_aff)

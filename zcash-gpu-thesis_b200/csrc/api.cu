@@ -87,7 +87,9 @@ int ctx_lanes(Ctx *ctx, int n) {
 }  // namespace b200zk
 
 #define CHECK_CTX(ctx) do { if (!(ctx)) return B200ZK_ERR_BAD_ARG; } while (0)
-#define USE_DEVICE(ctx) B200ZK_CUDA(ctx, cudaSetDevice((ctx)->device))
+#define USE_DEVICE(ctx)                                     \
+    std::lock_guard<std::recursive_mutex> ctx_lock__((ctx)->mu); \
+    B200ZK_CUDA(ctx, cudaSetDevice((ctx)->device))
 
 extern "C" {
 

@@ -239,9 +239,9 @@ int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_
     for (int j = 0; j < n_jobs; j++) {
         // job 0 (H) stays on the main stream; job j >= 1 goes to lane (j - 1) mod n_lanes
         Ctx *on = (j == 0 || n_lanes == 0) ? ctx : ctx->lanes[(j - 1) % n_lanes];
-        std::unique_lock<std::mutex> lk;
+        std::unique_lock<std::recursive_mutex> lk;
         if (on != ctx) {
-            lk = std::unique_lock<std::mutex>(on->mu);
+            lk = std::unique_lock<std::recursive_mutex>(on->mu);
             B200ZK_CUDA(ctx, cudaStreamWaitEvent(on->stream, ctx->ev_fork, 0));
         }
         const unsigned long long before = on->launches;

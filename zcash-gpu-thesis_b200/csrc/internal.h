@@ -42,7 +42,7 @@ struct Ctx {
     bool own_stream = true;
     int sm_count = 148;
     std::string last_error;
-    std::mutex mu;
+    std::recursive_mutex mu;  // every C-ABI entry holds it: calls on one context from several host threads are serialised
     std::map<uint32_t, NttTables> ntt_tables;
     // reusable scratch (grown on demand, stream-ordered use only)
     void *scratch = nullptr;
