@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
                                                    const uint32_t *__restrict__ rank, size_t base_offset, size_t n_bases,
                                                    const uint8_t *__restrict__ base_inf, MsmShape sh, MsmBatch batch,
                                                    uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted,
-                                                   uint32_t *__restrict__ status) {
+                                                   uint32_t *__restrict__ status, uint32_t slot_lo, uint32_t slot_hi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_exp) return;
     const uint32_t k = blockIdx.y;  // which multiexp of the batch
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
         if (d == 0) continue;
         // with precomputed 2^(c w) * P the digit of window w is a digit of window 0 for the point w * n + idx
         uint32_t slot = (k * sh.sets + (sh.pre_n ? 0u : w)) * sh.B + d - 1;
+        if (slot < slot_lo || slot >= slot_hi) continue;  // another pass of the scatter owns this bucket range
         if (MODE == 0) {
             atomicAdd(&counts_or_cursor[slot], 1u);
         } else {
@@ -504,10 +505,22 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
             ctx->launches += scan_u32<uint8_t>(st, d_density + k * batch.density_stride, n_exp, rank + k * (n_exp + 1), nullptr, sums);
     const dim3 eb((unsigned)((n_exp + 255) / 256), K);
     k_msm_digits<0><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, batch,
-                                        counts, nullptr, status);
+                                        counts, nullptr, status, 0u, 0xffffffffu);
     ctx->launches += scan_u32<uint32_t>(st, counts, nbk, offsets, cursor, sums);
-    k_msm_digits<1><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, batch,
-                                        cursor, sorted, status);
+    // The scatter writes 4-byte entries at random places of `sorted`; when that array is far larger than the L2 every entry
+    // costs a 32-byte read-modify-write in HBM.  Scattering one bucket range at a time (re-deriving the digits, which is
+    // cheap) keeps the live part of `sorted` L2-resident, so a bucket's entries merge into full sectors before they leave.
+    // Measured on B200 (2^22 ... 2^26 points): four passes save 3 % of the whole multiexp, more passes cost what they save.
+    const size_t sorted_bytes = refs_max * sizeof(uint32_t);
+    uint32_t passes = !use_pre ? 1u : sorted_bytes >= (256u << 20) ? 4u : sorted_bytes >= (128u << 20) ? 2u : 1u;
+    if (const char *e = getenv("B200ZK_SCATTER_PASSES")) passes = (uint32_t)std::max(1, atoi(e));
+    passes = std::max(1u, std::min<uint32_t>(passes, (uint32_t)nbk));
+    for (uint32_t ps = 0; ps < passes; ps++) {
+        const uint32_t lo = (uint32_t)((size_t)nbk * ps / passes), hi = (uint32_t)((size_t)nbk * (ps + 1) / passes);
+        k_msm_digits<1><<<eb, 256, 0, st>>>((const uint32_t *)d_scalars, n_exp, d_density, rank, base_offset, bases->n, bases->infinity, sh, batch,
+                                            cursor, sorted, status, lo, hi);
+    }
+    ctx->launches += passes - 1;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->prof_on) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
     if (use_ba) {
