@@ -802,7 +802,10 @@ int b200zk_groth16_prove_batch(b200zk_ctx *ctx, const b200zk_crs *crs, const b20
         return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument or bad lockstep");
     if (crs->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "CRS lives on another device");
     USE_DEVICE(ctx);
-    const size_t group = lockstep ? (size_t)lockstep : 8;
+    size_t group = lockstep ? (size_t)lockstep : 8;
+    // a batched multiexp indexes (proof, exponent, window) with 32 bits: large circuits are proved fewer at a time
+    const size_t largest = std::max<size_t>(std::max(n_constraints * 2, n_inputs + n_aux), 1);
+    group = std::max<size_t>(1, std::min(group, ((size_t)1 << 31) / (largest * 32)));
     std::vector<ProveArgs> args;
     for (size_t first = 0; first < n_proofs; first += group) {
         const size_t K = std::min(group, n_proofs - first);
