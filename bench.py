@@ -461,10 +461,13 @@ def bench_extra(w, zk, lib, rng, timed, world):
     for x in (a, b, c, o):
         x.free()
     out["sapling_spend_proofs"] = bench_spend_proofs(w, zk, rng, world)
+    # the reference's largest circuit: Sprout JoinSplit on Groth16, 1 989 085 constraints -> m = 2^21 (SURVEY.md section 8;
+    # sapling-crypto/src/circuit/sprout/mod.rs:465); variable counts and densities are not published: taken proportional to Spend's
+    out["sprout_joinsplit_shaped_proofs"] = bench_spend_proofs(w, zk, rng, world, shape=(1989085, 10, 1986000, 1719000, 1, 1234000))
     return out
 
 
-def bench_spend_proofs(w, zk, rng, world):
+def bench_spend_proofs(w, zk, rng, world, shape=None):
     """Sapling-Spend-shaped create_proof: 98 785 constraints -> m = 2^17; H 131 071, L 98 638, A 8 + 85 382,
     B 1 + 61 299 (G1 and G2) bases; witness-like scalars (half of them 0/1).  The CRS is synthetic ([k]G points generated on
     the device), so the proofs are not meaningful -- the arithmetic is identical to a real Spend proof.  Proofs of a batch
@@ -475,6 +478,10 @@ def bench_spend_proofs(w, zk, rng, world):
 
     n_con, n_in, n_aux = 98785, 8, 98638
     a_dense, b_in_dense, b_aux_dense = 85382, 1, 61299
+    light = shape is not None  # another circuit shape (the Sprout JoinSplit one): single-call latency and a short batch only
+    if light:
+        n_con, n_in, n_aux, a_dense, b_in_dense, b_aux_dense = shape
+    log_m = (n_con - 1).bit_length()
     g1 = gen_g1_limbs()
     g2 = gen_g2_limbs()
 
@@ -486,7 +493,7 @@ def bench_spend_proofs(w, zk, rng, world):
         dxy.free(); dinf.free()
         return b
 
-    h, l = bases(L.G1, (1 << 17) - 1, g1), bases(L.G1, n_aux, g1)
+    h, l = bases(L.G1, (1 << log_m) - 1, g1), bases(L.G1, n_aux, g1)
     a, b1, b2 = bases(L.G1, n_in + a_dense, g1), bases(L.G1, b_in_dense + b_aux_dense, g1), bases(L.G2, b_in_dense + b_aux_dense, g2)
     head1 = np.zeros((3, 12), dtype=np.uint64)
     st = w.lib.b200zk_d2h(w.ctx, head1.ctypes.data_as(ctypes.c_void_p), bases_ptr(w, zk, L.G1, g1, rng, 3), 3 * 96)
@@ -526,10 +533,23 @@ def bench_spend_proofs(w, zk, rng, world):
     p1 = prove(w)
     assert np.array_equal(p0.a, p1.a) and np.array_equal(p0.c, p1.c)  # deterministic
     t0 = time.perf_counter()
-    reps = 5
+    reps = 3 if light else 5
     for _ in range(reps):
         prove(w)
     single_ms = (time.perf_counter() - t0) / reps * 1e3
+    if light:
+        one = (ev[0], ev[1], ev[2], inputs, aux, da, dbi, dba, r, s)
+        ref = p0.write(w)
+        got = zk.create_proofs_from_assignments(w, params, [one] * 4, 4)
+        assert all(g.write(w) == ref for g in got)
+        t0 = time.perf_counter()
+        zk.create_proofs_from_assignments(w, params, [one] * 8, 4)
+        bdt = time.perf_counter() - t0
+        for q in (h, l, a, b1, b2):
+            q.free()
+        return {"single_call_ms_per_proof": single_ms, "proofs_per_s": world * 8 / bdt, "lockstep": 4, "batch": world * 8,
+                "shape": f"m=2^{log_m} ({n_con} constraints), multiexps {(1 << log_m) - 1}/{n_aux}/{n_in}+{a_dense}/{b_in_dense}+{b_aux_dense} (G1) and "
+                         f"{b_in_dense}+{b_aux_dense} (G2), synthetic CRS and densities", "crs_precompute_s": t_pre}
     streams = env_int("B200ZK_SPEND_STREAMS", 8)
     workers = [zk.Worker(w.device) for _ in range(streams)]
     for x in workers:
