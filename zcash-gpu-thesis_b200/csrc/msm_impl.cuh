@@ -181,6 +181,13 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
 #ifndef B200ZK_ACC_MINBLOCKS_G2
 #define B200ZK_ACC_MINBLOCKS_G2 2
 #endif
+#ifndef B200ZK_ACC_THREADS_G2
+#define B200ZK_ACC_THREADS_G2 128
+#endif
+template <class F> struct AccShape {
+    static constexpr unsigned THREADS = sizeof(F) > 48 ? B200ZK_ACC_THREADS_G2 : 128;
+    static constexpr unsigned MINBLOCKS = sizeof(F) > 48 ? B200ZK_ACC_MINBLOCKS_G2 : B200ZK_ACC_MINBLOCKS;
+};
 // Oversized buckets (witness scalars are full of 0/1/small values: half of a Sapling witness lands in bucket 1 of
 // window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
 // split bucket are folded by one warp (k_msm_combine_split).  Uniform scalars never split (cap = 2 x mean + slack).
@@ -208,7 +215,7 @@ static __global__ void k_msm_order_buckets(const uint32_t *__restrict__ offsets,
 }
 
 template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) > 48 ? B200ZK_ACC_MINBLOCKS_G2 : B200ZK_ACC_MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                        const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
                                                        const uint32_t *__restrict__ task_off, const uint32_t *__restrict__ order, uint32_t cap,
                                                        uint32_t max_tasks, XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ partials) {
@@ -456,7 +463,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         // dependent point addition).  Cut the chains so that there are about `waves` tasks per resident thread slot.
         double waves = 1.0;  // measured on Spend-shaped proofs: 1 beats 0.5, 2 and 4 on latency and on throughput
         if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
-        const size_t slots = (size_t)ctx->sm_count * (sizeof(F) > 48 ? B200ZK_ACC_MINBLOCKS_G2 : B200ZK_ACC_MINBLOCKS) * 128;
+        const size_t slots = (size_t)ctx->sm_count * AccShape<F>::MINBLOCKS * AccShape<F>::THREADS;
         if (waves > 0) {
             const size_t fill = (size_t)((double)refs_max / (waves * (double)slots));
             cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(8, fill));
@@ -538,7 +545,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
         ctx->launches += 8;  // digits x2, count_tasks, order_buckets, accumulate, combine_small, combine_big, window_combine
         k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
-        k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + 127) / 128), 128, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
+        k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + AccShape<F>::THREADS - 1) / AccShape<F>::THREADS), AccShape<F>::THREADS, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
                                                                                       task_cnt, task_off, order, cap, (uint32_t)max_tasks, buckets, partials);
         k_msm_combine_small<F><<<1024, 64, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
         const size_t big_smem = COMBINE_BIG_THREADS * sizeof(XYZZ<F>);  // 48 KiB (G1) / 96 KiB (G2) of dynamic shared memory
