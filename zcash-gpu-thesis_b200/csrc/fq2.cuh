@@ -19,8 +19,9 @@ struct fq2_t {
     __device__ __forceinline__ fq2_t neg() const { return {c0.neg(), c1.neg()}; }
     // fq2.rs:118-132
     __device__ __noinline__ friend fq2_t operator*(const fq2_t &a, const fq2_t &b) {
-        fq_t aa = a.c0 * b.c0;
-        fq_t bb = a.c1 * b.c1;
+        // a0 b0 and a1 b1 in one out-of-line body (two interleaved carry chains): 2 % on the G2 multiexp
+        fq_t::Pair p = fq_t::mul2_call(a.c0, b.c0, a.c1, b.c1);
+        const fq_t &aa = p.x, &bb = p.y;
         fq_t o = b.c0 + b.c1;
         fq_t c1 = (a.c1 + a.c0) * o;
         c1 = c1 - aa - bb;
@@ -28,10 +29,10 @@ struct fq2_t {
     }
     // fq2.rs:84-98
     __device__ __noinline__ fq2_t sqr() const {
-        fq_t ab = c0 * c1;
         fq_t s = c0 + c1;
         fq_t d = c0 - c1;
-        return {d * s, ab.dbl()};  // (c0-c1)(c0+c1) = c0^2 - c1^2 ;  2 c0 c1
+        fq_t::Pair p = fq_t::mul2_call(c0, c1, d, s);
+        return {p.y, p.x.dbl()};  // (c0-c1)(c0+c1) = c0^2 - c1^2 ;  2 c0 c1
     }
     __device__ fq2_t inverse() const {  // fq2.rs:134-153
         fq_t t = (c0.sqr() + c1.sqr()).inverse();

@@ -240,9 +240,11 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MINBLOCKS) 
             uint32_t mid = (lo + hi) >> 1;
             if (task_off[mid] <= task) lo = mid; else hi = mid;
         }
-        uint32_t j = task - task_off[lo];
-        beg = offsets[lo] + j * cap;
-        end = min(beg + cap, offsets[lo + 1]);
+        // the bucket's points are shared evenly among its tasks (equal chains, not cap, cap, ..., remainder)
+        const uint32_t j = task - task_off[lo], tasks = task_off[lo + 1] - task_off[lo];
+        const uint32_t first = offsets[lo], cnt = offsets[lo + 1] - first;
+        beg = first + (uint32_t)(((uint64_t)cnt * j) / tasks);
+        end = first + (uint32_t)(((uint64_t)cnt * (j + 1)) / tasks);
         dst = partials + task;
     }
     XYZZ<F> acc = XYZZ<F>::zero();
