@@ -192,11 +192,20 @@ template <class F> struct AccShape {
 // window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
 // split bucket are folded by one warp (k_msm_combine_split).  Uniform scalars never split (cap = 2 x mean + slack).
 static constexpr uint32_t SPLIT_SERIAL_MAX = 32;  // up to here one thread per bucket beats a block per bucket
-static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, uint32_t n_buckets, uint32_t cap, uint32_t *__restrict__ task_cnt,
+// The chain length above which a bucket is split, from the histogram itself: 1.25 x the ACTUAL mean load + 8, never above
+// the host's bound.  The nominal mean n W / buckets overestimates the typical load of a witness (half of its scalars are
+// 0 or 1 and contribute one digit or none), and the one or two heavy buckets would be cut into chains several times longer
+// than everybody else's: the whole kernel then waits for them (7.7 ms instead of ~3 for the batched G2 multiexp of 8 proofs).
+static __global__ void k_msm_pick_cap(const uint32_t *__restrict__ offsets, uint32_t n_buckets, uint32_t cap_host, uint32_t *__restrict__ cap_out) {
+    const uint32_t mean = offsets[n_buckets] / n_buckets;
+    *cap_out = max(8u, min(cap_host, mean + mean / 4 + 8));
+}
+static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ cap_dev, uint32_t *__restrict__ task_cnt,
                                          uint32_t *__restrict__ split_list, uint32_t *__restrict__ n_split, uint32_t *__restrict__ size_hist, uint32_t serial_max) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
     uint32_t cnt = offsets[b + 1] - offsets[b];
+    const uint32_t cap = *cap_dev;
     uint32_t tasks = cnt <= cap ? 0u : (cnt + cap - 1) / cap;
     task_cnt[b] = tasks;
     // n_split[0]: buckets with a few partial sums, listed from the front; n_split[1]: buckets with many, listed from the back
@@ -206,18 +215,19 @@ static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, u
 }
 // Counting sort of the bucket ids by load (fullest first): the 32 buckets of a warp then carry (almost) the same number of
 // points, so no lane idles while its neighbours finish (ncu: 29.2 of 32 lanes active before this, Poisson spread of the loads).
-static __global__ void k_msm_order_buckets(const uint32_t *__restrict__ offsets, uint32_t n_buckets, uint32_t cap, uint32_t *__restrict__ size_cursor,
+static __global__ void k_msm_order_buckets(const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ cap_dev, uint32_t *__restrict__ size_cursor,
                                            uint32_t *__restrict__ order) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
     uint32_t cnt = offsets[b + 1] - offsets[b];
+    const uint32_t cap = *cap_dev;
     order[atomicAdd(&size_cursor[cap - min(cnt, cap)], 1u)] = b;
 }
 
 template <class F>
 __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MINBLOCKS) k_msm_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                        const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
-                                                       const uint32_t *__restrict__ task_off, const uint32_t *__restrict__ order, uint32_t cap,
+                                                       const uint32_t *__restrict__ task_off, const uint32_t *__restrict__ order,
                                                        uint32_t max_tasks, XYZZ<F> *__restrict__ buckets, XYZZ<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t beg, end;
@@ -471,7 +481,8 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
             cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(8, fill));
         }
     }
-    const size_t max_tasks = (size_t)2 * refs_max / cap + 2;
+    // tasks <= 2 T / cap with the device's cap >= 1.25 T / buckets, hence <= 1.6 x buckets whatever the scalars are
+    const size_t max_tasks = std::max((size_t)2 * refs_max / cap, 2 * nbk) + 2;
     size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
     size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
     size_t o_shist = take((cap + 2) * sizeof(uint32_t)), o_scur = take((cap + 2) * sizeof(uint32_t)), o_order = take((nbk + 1) * sizeof(uint32_t));
@@ -542,13 +553,15 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         uint32_t *n_split = status + 4;  // two counters: few-partial buckets, many-partial buckets
         B200ZK_CUDA(ctx, cudaMemsetAsync(n_split, 0, 2 * sizeof(uint32_t), st));
         B200ZK_CUDA(ctx, cudaMemsetAsync(size_hist, 0, (cap + 2) * sizeof(uint32_t), st));
-        k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, task_cnt, split_list, n_split, size_hist, serial_max);
+        uint32_t *cap_dev = status + 6;
+        k_msm_pick_cap<<<1, 1, 0, st>>>(offsets, (uint32_t)nbk, cap, cap_dev);
+        k_msm_count_tasks<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap_dev, task_cnt, split_list, n_split, size_hist, serial_max);
         ctx->launches += scan_u32<uint32_t>(st, task_cnt, nbk, task_off, nullptr, sums);
         ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
-        ctx->launches += 8;  // digits x2, count_tasks, order_buckets, accumulate, combine_small, combine_big, window_combine
-        k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap, size_cur, order);
+        ctx->launches += 9;  // digits x2, pick_cap, count_tasks, order_buckets, accumulate, combine_small, combine_big, window_combine
+        k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap_dev, size_cur, order);
         k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + AccShape<F>::THREADS - 1) / AccShape<F>::THREADS), AccShape<F>::THREADS, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
-                                                                                      task_cnt, task_off, order, cap, (uint32_t)max_tasks, buckets, partials);
+                                                                                      task_cnt, task_off, order, (uint32_t)max_tasks, buckets, partials);
         k_msm_combine_small<F><<<1024, 64, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
         const size_t big_smem = COMBINE_BIG_THREADS * sizeof(XYZZ<F>);  // 48 KiB (G1) / 96 KiB (G2) of dynamic shared memory
         bool &opted_in = ctx->combine_smem_opt_in[sizeof(F) > 48 ? 1 : 0];
