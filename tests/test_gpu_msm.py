@@ -455,3 +455,44 @@ def test_one_context_shared_by_several_threads(worker):
         got_aff, got_inf = zk.into_affine(worker, zk.G1, got[t])
         want_aff, want_inf = cref.into_affine("g1", want)
         assert bool(got_inf[0]) == want_inf and np.array_equal(got_aff[0], want_aff)
+
+
+def test_two_devices_in_one_process(worker):
+    """A single host process (the reference's FFI caller) driving two GPUs: one context per device, used from two threads.
+    Skipped on a one-GPU box."""
+    import threading
+
+    import zcash_gpu_thesis_b200 as zk
+
+    if worker.lib.b200zk_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    r = util.rng(4400)
+    n = 5000
+    xy, _ = util.random_bases("g1", r, n)
+    exps = [util.random_fr_repr(r, n) for _ in range(2)]
+    got, errs = [None, None], []
+
+    def run(dev):
+        try:
+            w = worker if dev == 0 else zk.Worker(dev)
+            bases = zk.Bases(w, zk.G1, xy).precompute(0)
+            jac = zk.multiexp(w, (bases, 0), zk.FullDensity(), exps[dev])
+            got[dev] = zk.into_affine(w, zk.G1, jac)
+            d = zk.EvaluationDomain.from_coeffs(w, exps[dev][:1024] >> np.uint64(2))
+            d.fft(w); d.ifft(w)
+            bases.free()
+            if dev:
+                w.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=run, args=(d,)) for d in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for dev in range(2):
+        st, want = cref.multiexp("g1", xy, exps[dev])
+        want_aff, want_inf = cref.into_affine("g1", want)
+        assert st == 0 and bool(got[dev][1][0]) == want_inf and np.array_equal(got[dev][0][0], want_aff)
