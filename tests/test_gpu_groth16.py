@@ -187,3 +187,30 @@ def test_subversion_check(worker):
     asg = synthesize_assignment(E, Silly(2, 3))
     with pytest.raises(zk.UnexpectedIdentity):
         _gpu_prove(worker, dev, asg, 5, 6)
+
+
+def test_batch_round_robin_over_contexts(worker):
+    """sharding.prove_on_devices: lock-step groups of one batch go round-robin over several contexts (two GPUs when the box has
+    them, else two contexts of the one GPU); the proofs come back in order and equal the oracle's."""
+    import zcash_gpu_thesis_b200 as zk
+    from zcash_gpu_thesis_b200.sharding import lockstep_groups, prove_on_devices
+
+    assert lockstep_groups(7, 3) == [[0, 1, 2], [3, 4, 5], [6]] and lockstep_groups(0, 4) == []
+    E = BlsEngine
+    r0 = util.rng(2300)
+    rnd = lambda: util.rows_to_ints(util.random_fr_repr(r0, 1))[0]
+    consts = [rnd() for _ in range(10)]
+    params, _ = generate_parameters(E, MiMCLike(0, 0, consts), G1.gen, G2.gen, *[rnd() for _ in range(5)])
+    second = zk.Worker(1 if worker.lib.b200zk_device_count() > 1 else 0)
+    workers = [worker, second]
+    devs = [_upload(w, params) for w in workers]
+    batch, wants = [], []
+    for _ in range(7):
+        circ = MiMCLike(rnd(), rnd(), consts)
+        r, s = rnd(), rnd()
+        wants.append(proof_bytes(prove_from_assignment(E, synthesize_assignment(E, circ), params, r, s)))
+        batch.append(zk.synthesize(circ).as_tuple(r, s))
+    proofs = prove_on_devices(workers, devs, batch, lockstep=2)
+    assert [p.write(worker) for p in proofs] == wants
+    del devs
+    second.close()
