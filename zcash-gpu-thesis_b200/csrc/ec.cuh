@@ -25,6 +25,14 @@ struct Jacobian {  // ec.rs:20-24; identity <=> z == 0, canonical zero = (0, 1, 
     __device__ __forceinline__ bool is_zero() const { return z.is_zero(); }
 };
 
+// a*b - c*d: for Fq one fused out-of-line body with a single reduction (fp.cuh mulsub_call), otherwise two products
+template <class F>
+__device__ __forceinline__ F mul_sub(const F &a, const F &b, const F &c, const F &d) { return a * b - c * d; }
+#ifndef B200ZK_NO_FUSED_MULSUB  // measured: G1 MSM 2^24 81.1 -> 79.7 ms
+template <>
+__device__ __forceinline__ fq_t mul_sub<fq_t>(const fq_t &a, const fq_t &b, const fq_t &c, const fq_t &d) { return fq_t::mulsub_call(a, b, c, d); }
+#endif
+
 template <class F>
 struct XYZZ {
     F x, y, zz, zzz;
@@ -79,7 +87,7 @@ struct XYZZ {
         F ppp = pp_ * pp;
         F q = x * pp;
         F x3 = r.sqr() - ppp - q.dbl();
-        y = r * (q - x3) - y * ppp;
+        y = mul_sub(r, q - x3, y, ppp);
         x = x3;
         zz = zz * pp;
         zzz = zzz * ppp;

@@ -318,6 +318,23 @@ struct __align__(16) Fp {
     static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
     // Two independent products in one out-of-line body (used by the Fq2 product / squaring: one call instead of two,
     // 2 % on the G2 multiexp; pairing the products of the G1 point formulas the same way measured no gain).
+    // a*b - c*d with ONE Montgomery reduction: both products stay 2N limbs wide, T = a*b + (p^2 - c*d) < 2 p^2 < p R, and
+    // redc_wide brings it home (the Y3 of the point additions is such a difference: 156 multiplier instructions less).
+    // Only for parameter sets that define mod_sq (Fq).
+    static __device__ __noinline__ Fp mulsub_call(Fp a, Fp b, Fp c, Fp d) {
+        uint32_t T[2 * N], U[2 * N];
+        mul_rows<N>(U, c.v, d.v);
+        U[0] = sub_cc(P::mod_sq(0), U[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) U[k] = subc_cc(P::mod_sq(k), U[k]);
+        U[2 * N - 1] = subc(P::mod_sq(2 * N - 1), U[2 * N - 1]);
+        mul_rows<N>(T, a.v, b.v);
+        T[0] = add_cc(T[0], U[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) T[k] = addc_cc(T[k], U[k]);
+        T[2 * N - 1] = addc(T[2 * N - 1], U[2 * N - 1]);
+        return redc_wide(T);
+    }
     struct Pair { Fp x, y; };
     static __device__ __noinline__ Pair mul2_call(Fp a, Fp b, Fp c, Fp d) { return {mul_inline(a, b), mul_inline(c, d)}; }
     __device__ __forceinline__ static Fp mul_inline(const Fp &a, const Fp &b) {
