@@ -483,6 +483,21 @@ struct __align__(16) Fp {
     }
     // one reduction row: T += m p; T >>= 32 (roles of even / odd swap at the caller)
     __device__ __forceinline__ static void redc_row(uint32_t *even, uint32_t *odd, bool first) {
+#ifndef B200ZK_NO_FUSED_REDC_SHIFT
+        if (!first && !(P::mod(0) == 1u && P::mod(1) == 0xffffffffu)) {
+            // the two-limb shift of `odd` rides in the addend of its m * p products (as madc_n_rshift does for a * b):
+            // 12 carry additions less per row than shifting first and multiplying after
+            even[0] = add_cc(even[0], odd[1]);
+            const uint32_t mi = even[0] * B200ZK_M0_RT[P::N == 8 ? 0 : 1];  // a plain product: the carry flag survives it
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) { odd[j] = madc_lo_cc(P::mod(j + 1), mi, odd[j + 2]); odd[j + 1] = madc_hi_cc(P::mod(j + 1), mi, odd[j + 3]); }
+            odd[N - 2] = madc_lo_cc(P::mod(N - 1), mi, 0);
+            odd[N - 1] = madc_hi(P::mod(N - 1), mi, 0);
+            cmad_mod<0>(even, mi);
+            odd[N - 1] = addc(odd[N - 1], 0);
+            return;
+        }
+#endif
         if (!first) {
             even[0] = add_cc(even[0], odd[1]);  // stray limb; the carry is absorbed while odd shifts down by two limbs
 #pragma unroll
