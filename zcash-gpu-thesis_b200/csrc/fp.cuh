@@ -384,11 +384,10 @@ struct __align__(16) Fp {
                     E[i + j] = j == i + 2 ? mad_lo_cc(a.v[i], a.v[j], E[i + j]) : madc_lo_cc(a.v[i], a.v[j], E[i + j]);
                     E[i + j + 1] = madc_hi_cc(a.v[i], a.v[j], E[i + j + 1]);
                 }
-                constexpr int dummy = 0; (void)dummy;
-                const int last = i + (i + 2 + ((N - 1 - (i + 2)) / 2) * 2) + 1;  // limb of the last high half
-#pragma unroll
-                for (int k = last + 1; k < 2 * N - 1; k++) E[k] = addc_cc(E[k], 0);
-                if (last + 1 <= 2 * N - 1) E[2 * N - 1] = addc(E[2 * N - 1], 0);
+                // The chain ends in limb `last`.  Rows below reached at most limb `last` (and only as a high half), so the
+                // carry can spill one limb further, into a limb that is still zero: one addition, not a ripple to the top.
+                const int last = i + (i + 2 + ((N - 1 - (i + 2)) / 2) * 2) + 1;
+                if (last + 1 <= 2 * N - 1) E[last + 1] = addc(E[last + 1], 0);
             }
             {
 #pragma unroll
@@ -397,9 +396,7 @@ struct __align__(16) Fp {
                     O[i + j] = madc_hi_cc(a.v[i], a.v[j], O[i + j]);
                 }
                 const int last = i + (i + 1 + ((N - 1 - (i + 1)) / 2) * 2);
-#pragma unroll
-                for (int k = last + 1; k < 2 * N - 1; k++) O[k] = addc_cc(O[k], 0);
-                if (last + 1 <= 2 * N - 1) O[2 * N - 1] = addc(O[2 * N - 1], 0);
+                if (last + 1 <= 2 * N - 1) O[last + 1] = addc(O[last + 1], 0);
             }
         }
         // U = E + (O << 32), T = 2 U + sum a_i^2 2^(64 i)
