@@ -64,7 +64,7 @@ struct XYZZ {
         F xx = x.sqr();
         F m = xx.dbl() + xx;
         F x3 = m.sqr() - s.dbl();
-        y = m * (s - x3) - w * y;
+        y = mul_sub(m, s - x3, w, y);
         x = x3;
         zz = v * zz;
         zzz = w * zzz;
@@ -110,7 +110,7 @@ struct XYZZ {
         F ppp = pp_ * pp;
         F q = u1 * pp;
         F x3 = r.sqr() - ppp - q.dbl();
-        y = r * (q - x3) - s1 * ppp;
+        y = mul_sub(r, q - x3, s1, ppp);
         x = x3;
         zz = zz * o.zz * pp;
         zzz = zzz * o.zzz * ppp;
