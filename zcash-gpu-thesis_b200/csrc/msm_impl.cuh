@@ -196,6 +196,21 @@ static constexpr uint32_t SPLIT_SERIAL_MAX = 32;  // up to here one thread per b
 // the host's bound.  The nominal mean n W / buckets overestimates the typical load of a witness (half of its scalars are
 // 0 or 1 and contribute one digit or none), and the one or two heavy buckets would be cut into chains several times longer
 // than everybody else's: the whole kernel then waits for them (7.7 ms instead of ~3 for the batched G2 multiexp of 8 proofs).
+// atomicAdd(&counter[key], 1) for a warp whose lanes mostly share a few keys (bucket loads cluster around the mean): one
+// atomic per distinct key of the warp, every lane gets its own position.  All lanes of the warp must call it.
+__device__ __forceinline__ uint32_t warp_grouped_increment(uint32_t *counter, uint32_t key, bool active) {
+    const unsigned lanes = __ballot_sync(0xffffffffu, active);
+    uint32_t pos = 0;
+    if (active) {
+        const unsigned peers = __match_any_sync(lanes, key);
+        const unsigned lane = threadIdx.x & 31u, leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&counter[key], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        pos = base + __popc(peers & ((1u << lane) - 1u));
+    }
+    return pos;
+}
 static __global__ void k_msm_pick_cap(const uint32_t *__restrict__ offsets, uint32_t n_buckets, uint32_t cap_host, uint32_t *__restrict__ cap_out) {
     const uint32_t mean = offsets[n_buckets] / n_buckets;
     *cap_out = max(8u, min(cap_host, mean + mean / 4 + 8));
@@ -203,25 +218,29 @@ static __global__ void k_msm_pick_cap(const uint32_t *__restrict__ offsets, uint
 static __global__ void k_msm_count_tasks(const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ cap_dev, uint32_t *__restrict__ task_cnt,
                                          uint32_t *__restrict__ split_list, uint32_t *__restrict__ n_split, uint32_t *__restrict__ size_hist, uint32_t serial_max) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
-    uint32_t cnt = offsets[b + 1] - offsets[b];
+    const bool live = b < n_buckets;
     const uint32_t cap = *cap_dev;
-    uint32_t tasks = cnt <= cap ? 0u : (cnt + cap - 1) / cap;
-    task_cnt[b] = tasks;
-    // n_split[0]: buckets with a few partial sums, listed from the front; n_split[1]: buckets with many, listed from the back
-    if (tasks > serial_max) split_list[n_buckets - 1 - atomicAdd(n_split + 1, 1u)] = b;
-    else if (tasks) split_list[atomicAdd(n_split, 1u)] = b;
-    atomicAdd(&size_hist[cap - min(cnt, cap)], 1u);  // key 0 = fullest
+    uint32_t cnt = 0;
+    if (live) {
+        cnt = offsets[b + 1] - offsets[b];
+        uint32_t tasks = cnt <= cap ? 0u : (cnt + cap - 1) / cap;
+        task_cnt[b] = tasks;
+        // n_split[0]: buckets with a few partial sums, listed from the front; n_split[1]: buckets with many, listed from the back
+        if (tasks > serial_max) split_list[n_buckets - 1 - atomicAdd(n_split + 1, 1u)] = b;
+        else if (tasks) split_list[atomicAdd(n_split, 1u)] = b;
+    }
+    warp_grouped_increment(size_hist, cap - min(cnt, cap), live);  // key 0 = fullest
 }
 // Counting sort of the bucket ids by load (fullest first): the 32 buckets of a warp then carry (almost) the same number of
 // points, so no lane idles while its neighbours finish (ncu: 29.2 of 32 lanes active before this, Poisson spread of the loads).
 static __global__ void k_msm_order_buckets(const uint32_t *__restrict__ offsets, uint32_t n_buckets, const uint32_t *__restrict__ cap_dev, uint32_t *__restrict__ size_cursor,
                                            uint32_t *__restrict__ order) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
-    uint32_t cnt = offsets[b + 1] - offsets[b];
+    const bool live = b < n_buckets;
     const uint32_t cap = *cap_dev;
-    order[atomicAdd(&size_cursor[cap - min(cnt, cap)], 1u)] = b;
+    const uint32_t cnt = live ? offsets[b + 1] - offsets[b] : 0u;
+    const uint32_t pos = warp_grouped_increment(size_cursor, cap - min(cnt, cap), live);
+    if (live) order[pos] = b;
 }
 
 template <class F>

@@ -67,6 +67,11 @@ struct NttPass {
     int post_scale;   // 1: multiply stored element by consts[C_N_INV] (ifft); 2: by lo*hi tables (icoset_fft: g^-i / n)
 };
 
+// Tile layout in shared memory: two planes of 16-byte halves (limbs 0-3 of every element, then limbs 4-7).  Consecutive
+// threads touch consecutive 16-byte words of a plane, so an element moves with 2 conflict-free LDS.128 / STS.128 -- the
+// kernel is bound by instruction issue as much as by the multiplier (one butterfly = 114 wide multiplies x 4 issue
+// cycles against ~450 instructions), and the limb-major layout used before cost 32 LDS/STS.32 per butterfly instead of 8.
+#ifdef B200ZK_NTT_LIMB_MAJOR
 __device__ __forceinline__ fr_t sm_load(const uint32_t *sm, uint32_t tile, uint32_t e) {
     fr_t x;
 #pragma unroll
@@ -77,11 +82,26 @@ __device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t tile, uint32_t e
 #pragma unroll
     for (int l = 0; l < 8; l++) sm[l * tile + e] = x.v[l];
 }
+#else
+__device__ __forceinline__ fr_t sm_load(const uint32_t *sm, uint32_t tile, uint32_t e) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(sm);
+    const uint4 lo = p[e], hi = p[tile + e];
+    fr_t x;
+    x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w;
+    x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
+    return x;
+}
+__device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t tile, uint32_t e, const fr_t &x) {
+    uint4 *p = reinterpret_cast<uint4 *>(sm);
+    p[e] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    p[tile + e] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+#endif
 
 __global__ void __launch_bounds__(NTT_THREADS, 7) k_ntt_pass(const fr_t *__restrict__ in, fr_t *__restrict__ out, const fr_t *__restrict__ tw,
                                                          const fr_t *__restrict__ sc_lo, const fr_t *__restrict__ sc_hi,
                                                          const fr_t *__restrict__ consts, NttPass p) {
-    extern __shared__ uint32_t sm[];
+    extern __shared__ __align__(16) uint32_t sm[];
     const uint32_t T = p.B + p.q, TILE = 1u << T;
     const uint32_t tile = blockIdx.x;
     const uint32_t vshift = p.s0 == 0 ? 0 : p.q;
