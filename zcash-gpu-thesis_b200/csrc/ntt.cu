@@ -98,10 +98,18 @@ __device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t tile, uint32_t e
 }
 #endif
 
+#ifndef B200ZK_NTT_UNROLL
+#define B200ZK_NTT_UNROLL 1  // 2 and 4 measured no faster (3.86 / 3.88 / 3.88 ms at 2^24)
+#endif
+// CB / CQ: the pass shape as compile-time constants (0 = take it from `p`): the 2^24 transform runs three (8, 2) passes,
+// and with constant shifts the index arithmetic of a butterfly shrinks (the kernel is issue-bound, see sm_load).
+template <int CB, int CQ>
 __global__ void __launch_bounds__(NTT_THREADS, 7) k_ntt_pass(const fr_t *__restrict__ in, fr_t *__restrict__ out, const fr_t *__restrict__ tw,
                                                          const fr_t *__restrict__ sc_lo, const fr_t *__restrict__ sc_hi,
                                                          const fr_t *__restrict__ consts, NttPass p) {
     extern __shared__ __align__(16) uint32_t sm[];
+    if (CB) { p.B = CB; p.q = CQ; }
+    constexpr int UNROLL = CB ? B200ZK_NTT_UNROLL : 1;  // butterflies of one stage unrolled per thread (specialised shapes)
     const uint32_t T = p.B + p.q, TILE = 1u << T;
     const uint32_t tile = blockIdx.x;
     const uint32_t vshift = p.s0 == 0 ? 0 : p.q;
@@ -122,6 +130,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 7) k_ntt_pass(const fr_t *__restr
     __syncthreads();
     for (uint32_t k = 0; k < p.B; k++) {
         const uint32_t s = p.s0 + k, bitpos = k + vshift;
+#pragma unroll(UNROLL)
         for (uint32_t bf = threadIdx.x; bf < TILE / 2; bf += NTT_THREADS) {
             uint32_t lo = ((bf >> bitpos) << (bitpos + 1)) | (bf & ((1u << bitpos) - 1));
             uint32_t hi = lo | (1u << bitpos);
@@ -257,7 +266,11 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         uint32_t T = p.B + p.q;
         size_t smem = (size_t)8 * sizeof(uint32_t) << T;
         unsigned tiles = (unsigned)(n >> T);
-        k_ntt_pass<<<tiles, NTT_THREADS, smem, ctx->stream>>>(src, dst, tw, lo, hi, (const fr_t *)t->consts, p);
+#define B200ZK_NTT_SHAPE(CB, CQ) \
+    if (p.B == CB && p.q == CQ) k_ntt_pass<CB, CQ><<<tiles, NTT_THREADS, smem, ctx->stream>>>(src, dst, tw, lo, hi, (const fr_t *)t->consts, p); else
+        B200ZK_NTT_SHAPE(8, 2) B200ZK_NTT_SHAPE(7, 2) B200ZK_NTT_SHAPE(6, 2) B200ZK_NTT_SHAPE(5, 2)
+        k_ntt_pass<0, 0><<<tiles, NTT_THREADS, smem, ctx->stream>>>(src, dst, tw, lo, hi, (const fr_t *)t->consts, p);
+#undef B200ZK_NTT_SHAPE
         ctx->launches++;
         s0 += p.B;
     }
