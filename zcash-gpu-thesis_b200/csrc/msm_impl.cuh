@@ -492,7 +492,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     {
         // A small multiexp cannot fill the machine with one thread per bucket: its time is (longest chain) x (latency of one
         // dependent point addition).  Cut the chains so that there are about `waves` tasks per resident thread slot.
-        double waves = 1.0;  // measured on Spend-shaped proofs: 1 beats 0.5, 2 and 4 on latency and on throughput
+        double waves = 0.0;  // off: since the cap follows the actual histogram (k_msm_pick_cap) cutting every chain no longer pays (Spend proofs 250 vs 230 /s)
         if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
         const size_t slots = (size_t)ctx->sm_count * AccShape<F>::MINBLOCKS * AccShape<F>::THREADS;
         if (waves > 0) {
