@@ -55,7 +55,8 @@ enum { B200ZK_FFT = 0, B200ZK_IFFT = 1, B200ZK_COSET_FFT = 2, B200ZK_ICOSET_FFT 
 /* element-wise field ops (fr.rs / fq.rs); used by the parity tests and by EvaluationDomain::{mul,sub}_assign */
 enum {
     B200ZK_OP_ADD = 0, B200ZK_OP_SUB = 1, B200ZK_OP_MUL = 2, B200ZK_OP_SQUARE = 3, B200ZK_OP_DOUBLE = 4,
-    B200ZK_OP_NEGATE = 5, B200ZK_OP_INTO_REPR = 6, B200ZK_OP_FROM_REPR = 7, B200ZK_OP_INVERSE = 8
+    B200ZK_OP_NEGATE = 5, B200ZK_OP_INTO_REPR = 6, B200ZK_OP_FROM_REPR = 7, B200ZK_OP_INVERSE = 8,
+    B200ZK_OP_INVERSE_BINARY = 9 /* same value as INVERSE, by the reference's binary extended Euclid (fq.rs:849-903) */
 };
 /* point ops (ec.rs:296-526) for the parity tests */
 enum { B200ZK_POINT_DOUBLE = 0, B200ZK_POINT_ADD = 1, B200ZK_POINT_ADD_MIXED = 2 };

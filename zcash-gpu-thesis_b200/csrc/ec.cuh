@@ -137,6 +137,17 @@ __device__ inline bool jacobian_to_affine(const Jacobian<F> &p, Affine<F> &out) 
     return true;
 }
 
+// the same for a kernel in which ONE thread normalises one point (the proof assembly): serial binary-Euclid inversion
+template <class F>
+__device__ inline bool jacobian_to_affine_serial(const Jacobian<F> &p, Affine<F> &out) {
+    if (p.is_zero()) { out.x = F::zero(); out.y = F::one(); return false; }
+    F zi = p.z.inverse_binary();
+    F zi2 = zi.sqr();
+    out.x = p.x * zi2;
+    out.y = p.y * (zi2 * zi);
+    return true;
+}
+
 // Jacobian ops exactly as the reference does them -- used by the point-op parity kernels and the final
 // (tiny) cross-GPU / window sums where a Jacobian result is the API's output type.
 template <class F>

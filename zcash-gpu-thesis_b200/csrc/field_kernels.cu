@@ -24,6 +24,7 @@ __global__ void k_field_vec(int op, const F *__restrict__ a, const F *__restrict
     case B200ZK_OP_NEGATE: r = x.neg(); break;
     case B200ZK_OP_INTO_REPR: r = x.from_mont(); break;
     case B200ZK_OP_FROM_REPR: r = x.to_mont(); break;
+    case B200ZK_OP_INVERSE_BINARY: r = x.inverse_binary(); break;
     default: r = x.inverse(); break;
     }
     out[i] = r;
@@ -31,7 +32,7 @@ __global__ void k_field_vec(int op, const F *__restrict__ a, const F *__restrict
 
 int launch_field_vec(Ctx *ctx, int field, int op, const void *a, const void *b, void *out, size_t n) {
     if (n == 0) return B200ZK_OK;
-    if (op < 0 || op > B200ZK_OP_INVERSE) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field op");
+    if (op < 0 || op > B200ZK_OP_INVERSE_BINARY) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field op");
     unsigned blocks = (unsigned)((n + 127) / 128);
     if (field == B200ZK_FR)
         k_field_vec<fr_t><<<blocks, 128, 0, ctx->stream>>>(op, (const fr_t *)a, (const fr_t *)b, (fr_t *)out, n);

@@ -523,6 +523,50 @@ struct __align__(16) Fp {
         }
         return res;
     }
+    // Inverse by the binary extended Euclid the reference uses (fq.rs:849-903; b starts at R^2 so the result is already in
+    // Montgomery form).  Data-dependent loops, ~5x fewer cycles than the Fermat ladder for ONE thread: for the single-thread
+    // tails (proof assembly); full warps keep `inverse()`, whose control flow is uniform.  Same canonical value.  0 -> 0.
+    __device__ __noinline__ Fp inverse_binary() const {
+        if (is_zero()) return zero();
+        Fp u = *this, w, b = r2(), c = zero();
+#pragma unroll
+        for (int i = 0; i < N; i++) w.v[i] = P::mod(i);
+        auto is_one = [](const Fp &x) {
+            uint32_t rest = 0;
+            for (int i = 1; i < N; i++) rest |= x.v[i];
+            return rest == 0 && x.v[0] == 1u;
+        };
+        auto halve = [](Fp &x) {
+            for (int i = 0; i < N - 1; i++) x.v[i] = __funnelshift_r(x.v[i], x.v[i + 1], 1);
+            x.v[N - 1] >>= 1;
+        };
+        auto halve_mod = [&](Fp &x) {  // x / 2 mod p for x in [0, p): (x + p) / 2 when x is odd (x + p < 2^(32 N), no carry out)
+            if (x.v[0] & 1u) {
+                x.v[0] = add_cc(x.v[0], P::mod(0));
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) x.v[i] = addc_cc(x.v[i], P::mod(i));
+                x.v[N - 1] = addc(x.v[N - 1], P::mod(N - 1));
+            }
+            halve(x);
+        };
+        auto less = [](const Fp &x, const Fp &y) {
+            for (int i = N - 1; i >= 0; i--)
+                if (x.v[i] != y.v[i]) return x.v[i] < y.v[i];
+            return false;
+        };
+        auto sub_raw = [](Fp &x, const Fp &y) {  // x -= y, x >= y
+            x.v[0] = sub_cc(x.v[0], y.v[0]);
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) x.v[i] = subc_cc(x.v[i], y.v[i]);
+            x.v[N - 1] = subc(x.v[N - 1], y.v[N - 1]);
+        };
+        while (!is_one(u) && !is_one(w)) {
+            while (!(u.v[0] & 1u)) { halve(u); halve_mod(b); }
+            while (!(w.v[0] & 1u)) { halve(w); halve_mod(c); }
+            if (less(w, u)) { sub_raw(u, w); b = b - c; } else { sub_raw(w, u); c = c - b; }
+        }
+        return is_one(u) ? b : c;
+    }
     // inverse by Fermat (p-2).  Canonical, so it equals the reference's binary EEA (fq.rs:849-903).  0 -> 0.
     __device__ Fp inverse() const {
         uint32_t e[N];

@@ -68,6 +68,10 @@ struct fq2_t {
         fq_t::Pair p = fq_t::mul2_call(c0, c1, d, s);
         return {p.y, p.x.dbl()};  // (c0-c1)(c0+c1) = c0^2 - c1^2 ;  2 c0 c1
     }
+    __device__ fq2_t inverse_binary() const {  // as inverse(), with the serial Fq inversion (single-thread kernels)
+        fq_t t = (c0.sqr() + c1.sqr()).inverse_binary();
+        return {c0 * t, (c1 * t).neg()};
+    }
     __device__ fq2_t inverse() const {  // fq2.rs:134-153
         fq_t t = (c0.sqr() + c1.sqr()).inverse();
         return {c0 * t, (c1 * t).neg()};

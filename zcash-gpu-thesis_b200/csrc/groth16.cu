@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(32) k_proof_a(const g1_xyzz_t *table_d1, const
     t.add(g1_xyzz_t::from_jacobian(res_a[k]));
     const g1_jac_t ga = t.to_jacobian();
     g1_affine_t a;
-    bool ok = jacobian_to_affine(ga, a);
+    bool ok = jacobian_to_affine_serial(ga, a);
     proof_a[k] = a;
     inf_flags[4 * k + 0] = ok ? 0 : 1;
     sga[k] = jacobian_mul(ga, scal + 8);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(32) k_proof_b(const g2_xyzz_t *table_d2, const
     t.add_mixed(vk_g2[0], false);
     t.add(g2_xyzz_t::from_jacobian(res_b2[k]));
     g2_affine_t a;
-    bool ok = jacobian_to_affine(t.to_jacobian(), a);
+    bool ok = jacobian_to_affine_serial(t.to_jacobian(), a);
     proof_b[k] = a;
     inf_flags[4 * k + 1] = ok ? 0 : 1;
 }
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32) k_proof_c(const g1_jac_t *sga, const g1_ja
     jacobian_add(c, res_h[k]);
     jacobian_add(c, res_l[k]);
     g1_affine_t a;
-    bool ok = jacobian_to_affine(c, a);
+    bool ok = jacobian_to_affine_serial(c, a);
     proof_c[k] = a;
     inf_flags[4 * k + 2] = ok ? 0 : 1;
 }
