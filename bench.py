@@ -468,6 +468,26 @@ def bench_extra(w, zk, lib, rng, timed, world):
     return out
 
 
+def _slowest_rank(seconds, world):
+    """max over ranks of a wall-clock interval (every rank calls it at the same point), so that a multi-GPU proofs/s number is
+    all the proofs of the job over the time of the slowest rank"""
+    if world == 1:
+        return seconds
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _line_up(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
 def bench_spend_proofs(w, zk, rng, world, shape=None):
     """Sapling-Spend-shaped create_proof: 98 785 constraints -> m = 2^17; H 131 071, L 98 638, A 8 + 85 382,
     B 1 + 61 299 (G1 and G2) bases; witness-like scalars (half of them 0/1).  The CRS is synthetic ([k]G points generated on
@@ -543,9 +563,10 @@ def bench_spend_proofs(w, zk, rng, world, shape=None):
         ref = p0.write(w)
         got = zk.create_proofs_from_assignments(w, params, [one] * 4, 4)
         assert all(g.write(w) == ref for g in got)
+        _line_up(world)
         t0 = time.perf_counter()
         zk.create_proofs_from_assignments(w, params, [one] * 8, 4)
-        bdt = time.perf_counter() - t0
+        bdt = _slowest_rank(time.perf_counter() - t0, world)
         for q in (h, l, a, b1, b2):
             q.free()
         return {"single_call_ms_per_proof": single_ms, "proofs_per_s": world * 8 / bdt, "lockstep": 4, "batch": world * 8,
@@ -562,12 +583,13 @@ def bench_spend_proofs(w, zk, rng, world, shape=None):
             prove(x)
 
     ths = [threading.Thread(target=loop, args=(x,)) for x in workers]
+    _line_up(world)
     t0 = time.perf_counter()
     for t in ths:
         t.start()
     for t in ths:
         t.join()
-    dt = time.perf_counter() - t0
+    dt = _slowest_rank(time.perf_counter() - t0, world)
     for x in workers:
         x.close()
     # the batch API: `lockstep` proofs share five batched multiexps (b200zk_groth16_prove_batch); two contexts alternate so
@@ -586,19 +608,20 @@ def bench_spend_proofs(w, zk, rng, world, shape=None):
         zk.create_proofs_from_assignments(x, params, [one] * (lockstep * groups), lockstep)
 
     ths = [threading.Thread(target=bloop, args=(x,)) for x in bworkers]
+    _line_up(world)
     t0 = time.perf_counter()
     for t in ths:
         t.start()
     for t in ths:
         t.join()
-    bdt = time.perf_counter() - t0
+    bdt = _slowest_rank(time.perf_counter() - t0, world)
     for x in bworkers:
         x.close()
     batched = {"proofs_per_s": world * bstreams * lockstep * groups / bdt, "lockstep": lockstep, "contexts_per_gpu": bstreams,
                "batch": world * bstreams * lockstep * groups, "api": "b200zk_groth16_prove_batch"}
     return {"proofs_per_s": max(world * streams * per_thread / dt, batched["proofs_per_s"]), "batched": batched,
             "independent_calls_proofs_per_s": world * streams * per_thread / dt, "single_stream_ms_per_proof": single_ms, "streams_per_gpu": streams,
-            "batch": world * streams * per_thread, "timing": "host wall clock around b200zk_groth16_prove incl. H2D of a/b/c/assignments and D2H of the proof",
+            "batch": world * streams * per_thread, "timing": "host wall clock around the prove calls incl. H2D of a/b/c/assignments and D2H of the proofs; with N GPUs every rank proves its own share and the time is that of the slowest rank",
             "shape": "m=2^17, MSM sizes 131071/98638/8+85382/1+61299 (G1) and 1+61299 (G2), synthetic CRS",
             "crs_precompute_s": t_pre}
 
