@@ -190,7 +190,8 @@ template <class F> struct AccShape {
 };
 // Oversized buckets (witness scalars are full of 0/1/small values: half of a Sapling witness lands in bucket 1 of
 // window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
-// split bucket are folded by one warp (k_msm_combine_split).  Uniform scalars never split (cap = 2 x mean + slack).
+// split bucket are folded by k_msm_combine_small / k_msm_combine_big.  With uniform scalars only the few buckets that the
+// short top window feeds are split (the cap is 1.25 x the actual mean load + 8, k_msm_pick_cap).
 static constexpr uint32_t SPLIT_SERIAL_MAX = 32;  // up to here one thread per bucket beats a block per bucket
 // The chain length above which a bucket is split, from the histogram itself: 1.25 x the ACTUAL mean load + 8, never above
 // the host's bound.  The nominal mean n W / buckets overestimates the typical load of a witness (half of its scalars are
@@ -486,7 +487,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_rank = take(d_density ? K * (n_exp + 1) * sizeof(uint32_t) : 0);
     size_t o_sorted = take(refs_max * sizeof(uint32_t));
     size_t o_buckets = take(nbk * sizeof(XYZZ<F>));
-    // bucket splitting: cap = 2 x mean bucket load + 32; at most n*W/cap + nbk... split tasks, bounded by 2*n*W/cap
+    // bucket splitting: the host's bound on the cap (the device lowers it from the histogram, k_msm_pick_cap)
     const size_t mean_load = n_exp * (sh.W / sh.sets) / sh.B;
     uint32_t cap = (uint32_t)(mean_load + mean_load / 2 + 32);  // chains longer than ~1.5 x the mean are split
     {
