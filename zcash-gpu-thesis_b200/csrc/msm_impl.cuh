@@ -361,8 +361,13 @@ __global__ void __launch_bounds__(64) k_msm_reduce_level(const XYZZ<F> *__restri
 // Once a window is down to n <= SLICE_MAX entries (R_i, A_i) the 8-ary tree would still cost ~30 serial point operations
 // per level; a single thread needs ~10 us per point addition, so small multiexps (a Sapling proof's are ~10^5 points) were
 // spending most of their time here.  sum_i i R_i = sum_j 2^j T_j with T_j = sum over {i : bit j of i} R_i: all T_j, sum R_i and
-// sum A_i are plain sums, computed together by log8(n) levels of <= 8 additions (k_msm_slice_sum), then one short Horner.
+// sum A_i are plain sums, computed together by log2(n) levels of one addition each (k_msm_slice_sum; the levels are pure
+// latency: fan-in 2 measured faster than 3, 4 and 8 despite the extra launches), then the warp-parallel k_msm_slice_final.
 static constexpr uint32_t SLICE_MAX = 4096;
+#ifndef B200ZK_SLICE_FAN
+#define B200ZK_SLICE_FAN 2
+#endif
+static constexpr uint32_t SLICE_FAN = B200ZK_SLICE_FAN;  // entries folded per thread and level of the sliced sums
 // slice s < nb: masked sum of R (bit s of the index); s == nb: sum of R; s == nb + 1: sum of A.
 // first level: in = R / A arrays of n_in entries per window; later levels: in = previous Y ((nb + 2) rows of n_in per window)
 template <class F>
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(64) k_msm_slice_sum(const XYZZ<F> *__restrict_
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= W * S * n_out) return;
     uint32_t c = t % n_out, s = (t / n_out) % S, w = t / (n_out * S);
-    uint32_t first = c * 8, last = min(first + 8, n_in);
+    uint32_t first = c * SLICE_FAN, last = min(first + SLICE_FAN, n_in);
     XYZZ<F> acc = XYZZ<F>::zero();
     if (Yin) {
         const XYZZ<F> *src = Yin + ((size_t)w * S + s) * n_in;
@@ -530,8 +535,8 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     uint32_t slice_max = SLICE_MAX;
     if (const char *e = getenv("B200ZK_SLICE_MAX")) slice_max = (uint32_t)std::max(8, atoi(e));
     const size_t slice_n = std::min<size_t>(sh.B, slice_max);
-    const size_t y_entries = (size_t)bw * 18 * ((slice_n + 7) / 8) + 64;  // (nb + 2 <= 17) rows of n/8 sums per window
-    size_t o_y0 = take(y_entries * sizeof(XYZZ<F>)), o_y1 = take((y_entries / 8 + 64 * (size_t)bw * 18) * sizeof(XYZZ<F>));
+    const size_t y_entries = (size_t)bw * 18 * ((slice_n + SLICE_FAN - 1) / SLICE_FAN) + 64;  // (nb + 2 <= 17) rows of n / SLICE_FAN sums per window
+    size_t o_y0 = take(y_entries * sizeof(XYZZ<F>)), o_y1 = take((y_entries / SLICE_FAN + 64 * (size_t)bw * 18) * sizeof(XYZZ<F>));
     // batched-affine accumulation (msm_batched_affine.cuh): correct (the whole MSM suite passes with B200ZK_BA=1) but, as
     // measured on B200 at 2^24 (accumulation 90.5 ms vs 76.7 ms for the XYZZ kernel), slower: its two passes over the
     // points are bound by dependent gathers, not by the multiplier pipe.  Opt-in only.
@@ -633,7 +638,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         int yp = 0;
         uint32_t cur = n_in;
         do {
-            uint32_t n_out = (cur + 7) / 8;
+            uint32_t n_out = (cur + SLICE_FAN - 1) / SLICE_FAN;
             uint32_t threads = bw * S * n_out;
             k_msm_slice_sum<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, yin, cur, nb, n_out, bw, ys[yp]);
             ctx->launches++;
