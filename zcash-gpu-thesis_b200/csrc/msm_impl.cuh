@@ -278,10 +278,21 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MINBLOCKS) 
         dst = partials + task;
     }
     XYZZ<F> acc = XYZZ<F>::zero();
+    uint32_t e = beg < end ? sorted[beg] : 0u;
     for (uint32_t k = beg; k < end; k++) {
-        uint32_t e = sorted[k];
+        // the next reference is read one addition ahead and its point is requested from HBM while this addition runs
+        // (a prefetch costs no registers; the gather is a ~1 us dependent load in front of ~10 us of arithmetic)
+        const uint32_t e_next = k + 1 < end ? sorted[k + 1] : 0u;
+#ifndef B200ZK_NO_POINT_PREFETCH
+        if (k + 1 < end) {
+            const char *nxt = reinterpret_cast<const char *>(bases + (e_next & 0x7fffffffu));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + sizeof(Affine<F>) - 1));
+        }
+#endif
         Affine<F> p = bases[e & 0x7fffffffu];
         acc.add_mixed(p, (e >> 31) != 0);
+        e = e_next;
     }
     *dst = acc;
 }
