@@ -337,6 +337,8 @@ struct __align__(16) Fp {
     }
     struct Pair { Fp x, y; };
     static __device__ __noinline__ Pair mul2_call(Fp a, Fp b, Fp c, Fp d) { return {mul_inline(a, b), mul_inline(c, d)}; }
+    struct Triple { Fp x, y, z; };
+    static __device__ __noinline__ Triple mul3_call(Fp a, Fp b, Fp c, Fp d, Fp e, Fp f) { return {mul_inline(a, b), mul_inline(c, d), mul_inline(e, f)}; }
     __device__ __forceinline__ static Fp mul_inline(const Fp &a, const Fp &b) {
 #ifdef B200ZK_KARATSUBA
         if (N == 12) {
