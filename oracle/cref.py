@@ -145,3 +145,53 @@ def h_poly(a, b, c, threads=0):
     st = fn(_p(a), _p(b), _p(c), ctypes.c_uint32(log_m), _p(out), ctypes.c_int(threads))
     assert st == OK
     return out
+
+
+class ResidentBases:
+    """A base vector loaded once into the oracle's memory (the `Arc<Vec<G::Affine>>` a bellman caller keeps), so that a timed
+    multiexp does not include the conversion of the numpy array."""
+
+    def __init__(self, group, handle, n):
+        self.group, self.handle, self.n = group, handle, n
+
+    @classmethod
+    def load(cls, group, bases_xy, inf=None):
+        bases_xy = _u64(bases_xy)
+        fn = lib().cref_g1_bases_load if group == "g1" else lib().cref_g2_bases_load
+        fn.restype = ctypes.c_void_p
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8)
+        h = fn(_p(bases_xy), _p(inf), ctypes.c_size_t(bases_xy.shape[0]))
+        return cls(group, ctypes.c_void_p(h), bases_xy.shape[0])
+
+    @classmethod
+    def walk_g1(cls, start_xy, step_xy, n, n_first=0, threads=0):
+        """P_i = start + i * step, i < n, generated on the host cores (synthetic bases for the CPU arm of the bench).
+        Returns (handle, first n_first points as (n_first, 12) limbs)."""
+        fn = lib().cref_g1_bases_walk
+        fn.restype = ctypes.c_void_p
+        first = np.zeros((max(n_first, 1), 12), dtype=np.uint64)
+        h = fn(_p(_u64(start_xy)), _p(_u64(step_xy)), ctypes.c_size_t(n), _p(first), ctypes.c_size_t(n_first), ctypes.c_int(threads))
+        return cls("g1", ctypes.c_void_p(h), n), first[:n_first]
+
+    def multiexp(self, scalars, density=None, base_offset=0, threads=0):
+        scalars = _u64(scalars)
+        out = np.zeros(18 if self.group == "g1" else 36, dtype=np.uint64)
+        if density is not None:
+            density = np.ascontiguousarray(density, dtype=np.uint8)
+            assert density.shape[0] == scalars.shape[0]
+        fn = lib().cref_g1_multiexp_h if self.group == "g1" else lib().cref_g2_multiexp_h
+        fn.restype = ctypes.c_int
+        st = fn(self.handle, ctypes.c_size_t(base_offset), _p(scalars), ctypes.c_size_t(scalars.shape[0]), _p(density), _p(out), ctypes.c_int(threads))
+        return st, out
+
+    def free(self):
+        if self.handle is not None:
+            (lib().cref_g1_bases_free if self.group == "g1" else lib().cref_g2_bases_free)(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -518,6 +518,53 @@ int cref_g2_multiexp(const u64 *bases_xy, const uint8_t *inf, size_t nbases, siz
     if (st == CREF_OK) memcpy(out_jac, (void *)&r, 288);
     return st;
 }
+// ---- resident base vectors (an `Arc<Vec<G::Affine>>` the caller keeps, multiexp.rs:34-40): load once, time only multiexp()
+struct BasesG1 { std::vector<Aff<Fq>> v; };
+struct BasesG2 { std::vector<Aff<Fq2>> v; };
+void *cref_g1_bases_load(const u64 *xy, const uint8_t *inf, size_t n) { auto *b = new BasesG1(); load_aff(b->v, xy, inf, n); return b; }
+void *cref_g2_bases_load(const u64 *xy, const uint8_t *inf, size_t n) { auto *b = new BasesG2(); load_aff(b->v, xy, inf, n); return b; }
+void cref_g1_bases_free(void *h) { delete (BasesG1 *)h; }
+void cref_g2_bases_free(void *h) { delete (BasesG2 *)h; }
+int cref_g1_multiexp_h(const void *h, size_t base_offset, const u64 *scalars, size_t nexp, const uint8_t *density, u64 *out_jac, int threads) {
+    const auto &b = ((const BasesG1 *)h)->v;
+    Jac<Fq> r; int st = multiexp<Fq>(*get_worker(threads), b.data(), b.size(), base_offset, density, scalars, nexp, r);
+    if (st == CREF_OK) memcpy(out_jac, (void *)&r, 144);
+    return st;
+}
+int cref_g2_multiexp_h(const void *h, size_t base_offset, const u64 *scalars, size_t nexp, const uint8_t *density, u64 *out_jac, int threads) {
+    const auto &b = ((const BasesG2 *)h)->v;
+    Jac<Fq2> r; int st = multiexp<Fq2>(*get_worker(threads), b.data(), b.size(), base_offset, density, scalars, nexp, r);
+    if (st == CREF_OK) memcpy(out_jac, (void *)&r, 288);
+    return st;
+}
+// Synthetic base vector for the CPU arm of the bench (input preparation, not the timed path): P_i = start + i * step as affine
+// points, straight into a resident vector.  Chunks run on the pool; each normalises its Jacobian walk with one inversion
+// (batch_normalization, ec.rs:246-294).  Returns the handle; `first_xy` (optional) receives the first min(n, n_first) points.
+void *cref_g1_bases_walk(const u64 *start_xy, const u64 *step_xy, size_t n, u64 *first_xy, size_t n_first, int threads) {
+    Aff<Fq> s0, st; memcpy((void *)&s0.x, start_xy, 96); s0.inf = false; memcpy((void *)&st.x, step_xy, 96); st.inf = false;
+    auto *out = new BasesG1(); out->v.resize(n);
+    get_worker(threads)->scope(n, [&](size_t, size_t b, size_t e) {
+        u64 k[4] = {b, 0, 0, 0};
+        Jac<Fq> cur = affine_mul(st, k, 4);  // b * step
+        cur.add_assign_mixed(s0);
+        const size_t B = 1024;
+        std::vector<Jac<Fq>> blk(B); std::vector<Fq> pre(B);
+        for (size_t i0 = b; i0 < e; i0 += B) {
+            size_t cnt = std::min(B, e - i0);
+            Fq run = Fq::one();
+            for (size_t j = 0; j < cnt; j++) { blk[j] = cur; pre[j] = run; run.mul_assign(cur.z); cur.add_assign_mixed(st); }
+            Fq inv = run.inverse();
+            for (size_t j = cnt; j-- > 0;) {
+                Fq zi = inv; zi.mul_assign(pre[j]); inv.mul_assign(blk[j].z);
+                Fq zi2 = zi; zi2.square();
+                Aff<Fq> a; a.inf = false; a.x = blk[j].x; a.x.mul_assign(zi2); zi2.mul_assign(zi); a.y = blk[j].y; a.y.mul_assign(zi2);
+                out->v[i0 + j] = a;
+            }
+        }
+    });
+    for (size_t i = 0; i < std::min(n, n_first); i++) memcpy(first_xy + 12 * i, (void *)&out->v[i].x, 96);
+    return out;
+}
 // Jacobian (Montgomery limbs) -> affine x||y, returns 1 if infinity
 int cref_g1_into_affine(const u64 *jac, u64 *out_xy) { Jac<Fq> p; memcpy((void *)&p, jac, 144); Aff<Fq> a = p.into_affine(); memcpy(out_xy, (void *)&a.x, 96); return a.inf; }
 int cref_g2_into_affine(const u64 *jac, u64 *out_xy) { Jac<Fq2> p; memcpy((void *)&p, jac, 288); Aff<Fq2> a = p.into_affine(); memcpy(out_xy, (void *)&a.x, 192); return a.inf; }

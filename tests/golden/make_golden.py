@@ -6,6 +6,7 @@ Sources (all under /root/reference/librustzcash):
   pairing/src/bls12_381/fr.rs:1240-1262, 1306-1325     Fr mul / square KATs
   pairing/src/bls12_381/fq.rs:2558-2584, 2630-2651     Fq mul / square KATs
   pairing/src/bls12_381/ec.rs:1060-1175                G1 add / double KATs (canonical coordinates)
+  pairing/src/bls12_381/fq2.rs:273-681                 Fq2 square / mul / inverse / add / sub / negate / double KATs
   pairing/src/bls12_381/tests/*.dat                    1000 multiples of the generators, 4 encodings
   pairing/src/bls12_381/tests/mod.rs:5-53              pairing KAT e(G1, G2) (RELIC)
   bellman/src/groth16/tests/mod.rs:98-400              test_xordemo constants (DummyEngine, Fr = Z/64513)
@@ -51,6 +52,16 @@ def main():
     h = hexes("pairing/src/bls12_381/ec.rs", 1128, 1176)
     assert len(h) == 24
     out["g1_double"] = {"p": [h[0:6], h[6:12]], "dbl": [h[12:18], h[18:24]], "src": "ec.rs:1128-1175"}
+    # Fq2 KATs: canonical (from_repr) limbs, c0 then c1 of every element in source order
+    fq2 = {}
+    for name, lo, hi, parts in (("square", 273, 346, ("a", "out")), ("mul", 347, 410, ("a", "b", "out")), ("inverse", 411, 459, ("a", "out")),
+                                ("add", 460, 523, ("a", "b", "out")), ("sub", 524, 587, ("a", "b", "out")), ("negate", 588, 634, ("a", "out")),
+                                ("double", 635, 681, ("a", "out"))):
+        h = hexes("pairing/src/bls12_381/fq2.rs", lo, hi)
+        assert len(h) == 12 * len(parts), (name, len(h))
+        fq2[name] = {part: [h[12 * i:12 * i + 6], h[12 * i + 6:12 * i + 12]] for i, part in enumerate(parts)}
+        fq2[name]["src"] = f"fq2.rs:{lo}-{hi} (canonical limbs via from_repr; [c0, c1])"
+    out["fq2"] = fq2
     dat = {}
     for name, sz in (("g1_compressed", 48), ("g1_uncompressed", 96), ("g2_compressed", 96), ("g2_uncompressed", 192)):
         b = open(os.path.join(REF, f"pairing/src/bls12_381/tests/{name}_valid_test_vectors.dat"), "rb").read()

@@ -86,6 +86,64 @@ def test_field_kats(worker):
         assert np.array_equal(out, want)
 
 
+def _fq2_rows(vals):
+    """[(c0, c1), ...] canonical ints -> (n, 12) Montgomery limbs"""
+    return np.array([Fq.to_mont_limbs(c0) + Fq.to_mont_limbs(c1) for c0, c1 in vals], dtype=np.uint64)
+
+
+def test_fq2_ops_match_oracle_and_kats(worker):
+    """Fq2 directly (fq2.rs:84-205), not only through G2: every op on random + all edge pairs vs the restated Fq2, and the
+    reference's literal vectors fq2.rs:273-681 (square / mul / inverse / add / sub / negate / double)."""
+    import json
+    import os
+
+    import zcash_gpu_thesis_b200 as zk
+    from oracle.fields import Fq2
+
+    r = util.rng(5)
+    edge = [0, 1, 2, Fq.p - 1, Fq.p - 2, (Fq.p - 1) // 2, (Fq.p + 1) // 2, Fq.R % Fq.p]
+    pairs = [(x, y) for x in edge for y in edge]
+    rnd = util.rows_to_ints(util.random_field_canonical(r, Fq.p, 2 * 3000, 6))
+    pairs += list(zip(rnd[0::2], rnd[1::2]))
+    other = pairs[::-1]
+    a, b = _fq2_rows(pairs), _fq2_rows(other)
+    ops = dict(add=(0, Fq2.add), sub=(1, Fq2.sub), mul=(2, Fq2.mul))
+    for name, (code, fn) in ops.items():
+        got = zk.field_vec(worker, zk.FQ2, code, a, b)
+        want = _fq2_rows([fn(x, y) for x, y in zip(pairs, other)])
+        assert np.array_equal(got, want), name
+    for name, code, fn in (("square", 3, Fq2.sqr), ("double", 4, lambda x: Fq2.add(x, x)), ("negate", 5, Fq2.neg)):
+        got = zk.field_vec(worker, zk.FQ2, code, a)
+        assert np.array_equal(got, _fq2_rows([fn(x) for x in pairs])), name
+    some = [p for p in pairs if p != (0, 0)][:400]
+    for code in (8, 9):
+        got = zk.field_vec(worker, zk.FQ2, code, _fq2_rows(some))
+        assert np.array_equal(got, _fq2_rows([Fq2.inv(x) for x in some])), code
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))["fq2"]
+    el = lambda v: (sum(int(x, 16) << (64 * i) for i, x in enumerate(v[0])), sum(int(x, 16) << (64 * i) for i, x in enumerate(v[1])))
+    for name, code in (("square", 3), ("mul", 2), ("inverse", 8), ("add", 0), ("sub", 1), ("negate", 5), ("double", 4)):
+        k = kat[name]
+        got = zk.field_vec(worker, zk.FQ2, code, _fq2_rows([el(k["a"])]), _fq2_rows([el(k["b"])]) if "b" in k else None)
+        assert np.array_equal(got, _fq2_rows([el(k["out"])])), f"fq2.rs KAT {name}"
+
+
+def test_fq_mulsub_matches_oracle(worker):
+    """a b - c d with one Montgomery reduction (fp.cuh mulsub_call, the Y3 of every point addition): random and all edge
+    quadruples, incl. a b = c d, c d = 0 and operands p - 1 (the q^2 - c d offset must never wrap)."""
+    import zcash_gpu_thesis_b200 as zk
+
+    r = util.rng(6)
+    e = _edge(Fq, 6)
+    k = len(e)
+    idx = np.array([(i, j, u, v) for i in range(k) for j in range(k) for u in range(k) for v in range(k)])
+    ab = np.concatenate([np.concatenate([e[idx[:, 0]], e[idx[:, 1]]], axis=1), util.random_field_canonical(r, Fq.p, 2 * 50_000, 6).reshape(-1, 12)])
+    cd = np.concatenate([np.concatenate([e[idx[:, 2]], e[idx[:, 3]]], axis=1), util.random_field_canonical(r, Fq.p, 2 * 50_000, 6).reshape(-1, 12)])
+    ab[-1], cd[-1] = ab[-2], ab[-2]  # a b - a b = 0
+    got = zk.field_vec(worker, zk.FQ, zk._lib.OP_MULSUB, ab, cd)
+    want = cref.field_vec("fq", "sub", cref.field_vec("fq", "mul", ab[:, :6], ab[:, 6:]), cref.field_vec("fq", "mul", cd[:, :6], cd[:, 6:]))
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("group", ["g1", "g2"])
 def test_point_ops_match_oracle(worker, group):
     """double / add_assign / add_assign_mixed incl. the exceptional branches of ec.rs:446-526."""

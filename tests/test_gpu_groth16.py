@@ -214,3 +214,60 @@ def test_batch_round_robin_over_contexts(worker):
     assert [p.write(worker) for p in proofs] == wants
     del devs
     second.close()
+
+
+def _spend_crs(worker, rng, shape):
+    """Synthetic CRS of a circuit shape: query vectors [k_i]G generated on the device (checked against the oracle on a sample)
+    and downloaded, so that the GPU prover and the CPU oracle consume the same arrays."""
+    import zcash_gpu_thesis_b200 as zk
+    from oracle import cref, spend
+    from tools import synthetic as syn
+
+    sizes = syn.crs_sizes(shape)
+    host, dev = {}, {}
+    for name, n in sizes.items():
+        group, gen, gname, w = (zk.G2, util.g2_gen_limbs(), "g2", 24) if name == "b_g2" else (zk.G1, util.g1_gen_limbs(), "g1", 12)
+        k = syn.base_multipliers(rng, n)
+        dxy, dinf, _ = zk.fixed_base_mul(worker, group, gen, k, 64)
+        xy = dxy.download(np.uint64, n * w).reshape(n, w)
+        pick = rng.choice(n, size=8, replace=False)
+        want, _ = cref.scalar_muls(gname, gen, k[pick])
+        assert np.array_equal(xy[pick], want)
+        host[name] = xy
+        dev[name] = zk.Bases.from_device(worker, group, dxy, n)
+        dxy.free(); dinf.free()
+    vk1, _ = cref.scalar_muls("g1", util.g1_gen_limbs(), syn.base_multipliers(rng, 3))   # alpha_g1, beta_g1, delta_g1
+    vk2, _ = cref.scalar_muls("g2", util.g2_gen_limbs(), syn.base_multipliers(rng, 2))   # beta_g2, delta_g2
+    params = zk.Parameters(worker, dev["h"], dev["l"], dev["a"], dev["b_g1"], dev["b_g2"], vk1[0], vk1[1], vk2[0], vk1[2], vk2[1])
+    crs = spend.HostCrs(host["h"], host["l"], host["a"], host["b_g1"], host["b_g2"], vk1[0], vk1[1], vk2[0], vk1[2], vk2[1])
+    return params, crs, dev
+
+
+@pytest.mark.parametrize("precompute", [False, True])
+def test_spend_shaped_proof_matches_oracle(worker, precompute):
+    """BASELINE config 5 at its real size (m = 2^17, multiexps of 131 071 / 98 638 / 8 + 85 382 / 1 + 61 299 bases, witness-like
+    scalars, random density maps): the 192 proof bytes of the GPU prover -- single call and lock-step 8 -- equal the CPU oracle's
+    (C++ port of the H block and of the reference's eight multiexps + the restated assembly of prover.rs:326-363)."""
+    import zcash_gpu_thesis_b200 as zk
+    from oracle import spend
+    from tools import synthetic as syn
+
+    r0 = util.rng(2400)
+    params, crs, dev = _spend_crs(worker, r0, syn.SPEND_SHAPE)
+    if precompute:
+        for b in dev.values():
+            b.precompute(0)
+    asgs = [syn.spend_assignment(r0) for _ in range(3)]
+    answers = [spend.multiexp_phase(crs, a) for a in asgs]
+    rnd = lambda: util.rows_to_ints(util.random_fr_repr(r0, 1))[0]
+    order = ("a", "b", "c", "inputs", "aux", "a_aux_density", "b_input_density", "b_aux_density")
+    r, s = rnd(), rnd()
+    got = zk.create_proof_from_assignment(worker, params, *[asgs[0][k] for k in order], r, s)
+    assert got.write(worker) == spend.assemble(crs, answers[0], r, s)
+    batch, wants = [], []
+    for k in range(8):
+        r, s = rnd(), rnd()
+        batch.append(tuple(asgs[k % 3][f] for f in order) + (r, s))
+        wants.append(spend.assemble(crs, answers[k % 3], r, s))
+    proofs = zk.create_proofs_from_assignments(worker, params, batch, lockstep=8)
+    assert [p.write(worker) for p in proofs] == wants

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 KINDS = [(0, "fft"), (1, "ifft"), (2, "coset_fft"), (3, "icoset_fft")]
 
 
-@pytest.mark.parametrize("log_m", list(range(0, 15)) + [16, 17, 18, 20])
+@pytest.mark.parametrize("log_m", list(range(0, 21)))
 def test_ntt_matches_serial_fft(worker, log_m):
     """Every transform kind at 2^0..2^20: device output == oracle serial_fft output, every limb."""
     import zcash_gpu_thesis_b200 as zk
@@ -65,6 +65,22 @@ def test_ntt_2_24_round_trip_and_spot_check(worker):
         assert zk.bellman.fr_from_mont_limbs(X[k]) == want, f"X[{k}]"
     d.ifft(worker)
     assert np.array_equal(d.into_coeffs(), x)
+
+
+@pytest.mark.parametrize("log_m", [21, 22, 23, 24])
+def test_ntt_large_all_kinds_full_compare(worker, log_m):
+    """2^21..2^24 (the headline size): all four transform kinds, every limb of every output against the oracle's best_fft
+    (domain.rs:261-270: parallel_fft on the host threads; == serial_fft by tests/test_oracle_golden.py) -- this covers the
+    coset tables (g^i, g^-i / m) over the full index range."""
+    import zcash_gpu_thesis_b200 as zk
+
+    m = 1 << log_m
+    coeffs = util.random_fr_mont(util.rng(500 + log_m), m)
+    for kind, name in KINDS:
+        got = zk.ntt_host(worker, coeffs, kind)
+        want = cref.fft(coeffs, kind, serial=False)
+        assert np.array_equal(got, want), f"{name} at 2^{log_m}"
+        del got, want
 
 
 def test_polynomial_arith(worker):

@@ -270,3 +270,74 @@ def test_pairing_kat_and_groth16_verify():
     proof = create_proof(E, Silly(6, 7), params, 99, 101)
     assert verify_proof(E, params.vk, proof, [42])
     assert not verify_proof(E, params.vk, proof, [43])
+
+
+def test_spend_oracle_equals_pipeline_oracle():
+    """oracle/spend.py (C++ H block + the reference's eight multiexps + restated assembly, used for Spend-sized circuits) gives the
+    192 bytes of oracle/groth16.prove_from_assignment (pinned by the xordemo KAT above) on a MiMC circuit."""
+    import random
+
+    import numpy as np
+
+    from oracle import spend
+    from oracle.curve import G1, G2
+    from oracle.fields import Fr, int_to_limbs
+    from oracle.groth16 import generate_parameters, proof_bytes, prove_from_assignment, synthesize_assignment
+    from oracle.pairing import Bls12
+    from tests.test_gpu_groth16 import MiMCLike
+
+    R = random.Random(5)
+    rnd = lambda: R.randrange(Fr.p)
+    consts = [rnd() for _ in range(8)]
+    params, _ = generate_parameters(Bls12, MiMCLike(0, 0, consts), G1.gen, G2.gen, *[rnd() for _ in range(5)])
+    asg = synthesize_assignment(Bls12, MiMCLike(rnd(), rnd(), consts))
+    pack = lambda G, v: np.array([G.affine_to_limbs(p) for p in v], dtype=np.uint64).reshape(len(v), -1)
+    al = lambda G, p: np.array(G.affine_to_limbs(p), dtype=np.uint64)
+    vk = params.vk
+    crs = spend.HostCrs(pack(G1, params.h), pack(G1, params.l), pack(G1, params.a), pack(G1, params.b_g1), pack(G2, params.b_g2),
+                        al(G1, vk.alpha_g1), al(G1, vk.beta_g1), al(G2, vk.beta_g2), al(G1, vk.delta_g1), al(G2, vk.delta_g2))
+    mont = lambda v: np.array([Fr.to_mont_limbs(x) for x in v], dtype=np.uint64).reshape(len(v), 4)
+    rep = lambda v: np.array([int_to_limbs(x, 4) for x in v], dtype=np.uint64).reshape(len(v), 4)
+    u8 = lambda v: np.array(v, dtype=np.uint8)
+    d = dict(a=mont(asg.a), b=mont(asg.b), c=mont(asg.c), inputs=rep(asg.input_assignment), aux=rep(asg.aux_assignment),
+             a_aux_density=u8(asg.a_aux_density), b_input_density=u8(asg.b_input_density), b_aux_density=u8(asg.b_aux_density))
+    for _ in range(2):
+        r, s = rnd(), rnd()
+        assert spend.prove(crs, d, r, s)[0] == proof_bytes(prove_from_assignment(Bls12, asg, params, r, s))
+
+
+def test_walk_bases_and_resident_multiexp():
+    """the CPU arm's synthetic base generator (P_i = start + i * step) and the handle-based multiexp equal the plain entry points"""
+    import numpy as np
+
+    from oracle import cref
+    from tests import util
+
+    gen = util.g1_gen_limbs()
+    step, _ = cref.scalar_muls("g1", gen, np.array([[7, 0, 0, 0]], dtype=np.uint64))
+    n = 3000
+    h, first = cref.ResidentBases.walk_g1(gen, step[0], n, n)
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    ks[:, 0] = 1 + 7 * np.arange(n, dtype=np.uint64)
+    want, _ = cref.scalar_muls("g1", gen, ks)
+    assert np.array_equal(first, want)
+    exps = util.random_fr_repr(util.rng(77), n)
+    st1, a = h.multiexp(exps)
+    st2, b = cref.multiexp("g1", want, exps)
+    assert st1 == 0 and st2 == 0 and np.array_equal(a, b)
+
+
+def test_fq2_kats():
+    """fq2.rs:273-681 literal vectors against the restated Fq2 (oracle/fields.py) and the C++ port is exercised through G2"""
+    import json
+    import os
+
+    from oracle.fields import Fq2
+
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))["fq2"]
+    el = lambda v: (sum(int(x, 16) << (64 * i) for i, x in enumerate(v[0])), sum(int(x, 16) << (64 * i) for i, x in enumerate(v[1])))
+    fns = dict(square=lambda a: Fq2.sqr(a), mul=Fq2.mul, inverse=Fq2.inv, add=Fq2.add, sub=Fq2.sub, negate=Fq2.neg, double=lambda a: Fq2.add(a, a))
+    for name, fn in fns.items():
+        k = kat[name]
+        args = [el(k["a"])] + ([el(k["b"])] if "b" in k else [])
+        assert fn(*args) == el(k["out"]), name

@@ -563,10 +563,12 @@ def encode_points(worker, group, xy, inf=None, compressed=False) -> bytes:
 
 # ------------------------------------------------------------------------------------------------------ test / bench helpers
 def field_vec(worker, field, op, a, b=None):
-    w = 4 if field == L.FR else 6
-    a = _u64(a, w)
-    b = None if b is None else _u64(b, w)
-    out = np.empty_like(a)
+    """element-wise Fr / Fq / Fq2 ops on host arrays; OP_MULSUB (Fq): rows of a are (p, q), rows of b are (r, s), out = p q - r s"""
+    w = {L.FR: 4, L.FQ: 6, L.FQ2: 12}[field]
+    wi = 2 * w if op == L.OP_MULSUB else w
+    a = _u64(a, wi)
+    b = None if b is None else _u64(b, wi)
+    out = np.empty((a.shape[0], w), dtype=np.uint64)
     st = worker.lib.b200zk_field_vec(worker.ctx, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0])
     if st:
         _raise(worker, st)

@@ -669,9 +669,10 @@ int b200zk_field_vec_dev(b200zk_ctx *ctx, int field, int op, const void *d_a, co
 
 int b200zk_field_vec(b200zk_ctx *ctx, int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
     CHECK_CTX(ctx);
-    if (field != B200ZK_FR && field != B200ZK_FQ) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field");
+    if (field != B200ZK_FR && field != B200ZK_FQ && field != B200ZK_FQ2) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field");
     USE_DEVICE(ctx);
-    const size_t eb = field == B200ZK_FR ? 32 : 48;
+    const size_t ob = field == B200ZK_FR ? 32 : field == B200ZK_FQ ? 48 : 96;  // bytes per output element
+    const size_t eb = op == B200ZK_OP_MULSUB ? 2 * ob : ob;                      // MULSUB reads pairs
     const size_t bytes = (n * eb + 255) / 256 * 256;
     int rc = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, 3 * bytes + 256);
     if (rc) return rc;
@@ -680,7 +681,7 @@ int b200zk_field_vec(b200zk_ctx *ctx, int field, int op, const uint64_t *a, cons
     if (n && b) B200ZK_CUDA(ctx, cudaMemcpyAsync(s + bytes, b, n * eb, cudaMemcpyHostToDevice, ctx->stream));
     rc = launch_field_vec(ctx, field, op, s, b ? s + bytes : s, s + 2 * bytes, n);
     if (rc) return rc;
-    if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(out, s + 2 * bytes, n * eb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(out, s + 2 * bytes, n * ob, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
 }

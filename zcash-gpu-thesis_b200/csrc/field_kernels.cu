@@ -30,11 +30,47 @@ __global__ void k_field_vec(int op, const F *__restrict__ a, const F *__restrict
     out[i] = r;
 }
 
+// Fq2 (fq2.rs:84-205): the same op codes on c0||c1 elements.  The two repr conversions act per component.
+__global__ void k_fq2_vec(int op, const fq2_t *__restrict__ a, const fq2_t *__restrict__ b, fq2_t *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fq2_t x = a[i];
+    fq2_t r;
+    switch (op) {
+    case B200ZK_OP_ADD: r = x + b[i]; break;
+    case B200ZK_OP_SUB: r = x - b[i]; break;
+    case B200ZK_OP_MUL: r = x * b[i]; break;
+    case B200ZK_OP_SQUARE: r = x.sqr(); break;
+    case B200ZK_OP_DOUBLE: r = x.dbl(); break;
+    case B200ZK_OP_NEGATE: r = x.neg(); break;
+    case B200ZK_OP_INTO_REPR: r = {x.c0.from_mont(), x.c1.from_mont()}; break;
+    case B200ZK_OP_FROM_REPR: r = {x.c0.to_mont(), x.c1.to_mont()}; break;
+    case B200ZK_OP_INVERSE_BINARY: r = x.inverse_binary(); break;
+    default: r = x.inverse(); break;
+    }
+    out[i] = r;
+}
+// a[i] = (p, q), b[i] = (r, s) as pairs of Fq elements; out[i] = p q - r s by the fused one-reduction body that every point
+// addition uses for its Y3 (fp.cuh mulsub_call)
+__global__ void k_fq_mulsub(const fq_t *__restrict__ a, const fq_t *__restrict__ b, fq_t *__restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fq_t::mulsub_call(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+}
+
 int launch_field_vec(Ctx *ctx, int field, int op, const void *a, const void *b, void *out, size_t n) {
     if (n == 0) return B200ZK_OK;
-    if (op < 0 || op > B200ZK_OP_INVERSE_BINARY) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field op");
     unsigned blocks = (unsigned)((n + 127) / 128);
-    if (field == B200ZK_FR)
+    if (op == B200ZK_OP_MULSUB) {
+        if (field != B200ZK_FQ) return set_error(ctx, B200ZK_ERR_BAD_ARG, "MULSUB is an Fq op");
+        k_fq_mulsub<<<blocks, 128, 0, ctx->stream>>>((const fq_t *)a, (const fq_t *)b, (fq_t *)out, n);
+        B200ZK_CUDA(ctx, cudaGetLastError());
+        return B200ZK_OK;
+    }
+    if (op < 0 || op > B200ZK_OP_INVERSE_BINARY) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field op");
+    if (field == B200ZK_FQ2)
+        k_fq2_vec<<<blocks, 128, 0, ctx->stream>>>(op, (const fq2_t *)a, (const fq2_t *)b, (fq2_t *)out, n);
+    else if (field == B200ZK_FR)
         k_field_vec<fr_t><<<blocks, 128, 0, ctx->stream>>>(op, (const fr_t *)a, (const fr_t *)b, (fr_t *)out, n);
     else if (field == B200ZK_FQ)
         k_field_vec<fq_t><<<blocks, 128, 0, ctx->stream>>>(op, (const fq_t *)a, (const fq_t *)b, (fq_t *)out, n);
