@@ -170,8 +170,44 @@ int b200zk_fixed_base_mul_dev(b200zk_ctx *ctx, int group, const uint64_t *base_a
 int b200zk_nccl_unique_id(uint8_t out_id[128]);
 int b200zk_comm_init(b200zk_ctx *ctx, const uint8_t unique_id[128], int rank, int world);
 /* Each rank passes the partial Jacobian sum of its shard (device); all ranks receive the total (device).
- * ncclAllGather of 144/288 B per rank on the context's stream followed by a (world-1)-add kernel. */
+ * ncclAllGather of one 320-byte record (point + status word) per rank on the context's stream followed by a (world-1)-add kernel.
+ * In b200zk_multiexp_sharded_async the shard's last kernel writes its record straight into the send slot, and the status words
+ * are reduced with the points: an UnexpectedIdentity / UnexpectedEof of any shard is returned by every rank. */
 int b200zk_allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total);
+
+/* ---- one process, several GPUs ------------------------------------------------------------------------------------------
+ * The reference's only product caller issues all the multiexps of a proof from ONE process (prover.rs:289-318, reached from the C
+ * ABI at librustzcash/src/rustzcash.rs:1556), so a drop-in must use several GPUs from one process: a *group* holds one context
+ * per entry of `devices` (an entry may repeat: two shards on one GPU).  Bases are sharded by contiguous range over the group's
+ * devices at upload; a multiexp cuts its exponent vector where the base cursor crosses a shard boundary (density-aware, see
+ * b200zk_multi_plan), runs the shards concurrently and sums the per-shard partials on the first device -- the last kernel of a
+ * shard stores its partial straight into the first device's memory over NVLink when peer access is available.  Semantics and
+ * status codes are those of b200zk_multiexp (the first offending exponent in iteration order decides, whatever shard it is in). */
+typedef struct b200zk_group b200zk_group;
+typedef struct b200zk_group_bases b200zk_group_bases;
+typedef struct b200zk_group_job b200zk_group_job;
+int b200zk_init_multi(const int *devices, int n_dev, b200zk_group **out);
+void b200zk_group_destroy(b200zk_group *g);
+const char *b200zk_group_last_error(b200zk_group *g);
+int b200zk_group_size(const b200zk_group *g);
+b200zk_ctx *b200zk_group_ctx(b200zk_group *g, int i);        /* the context of shard i (for NTTs / proofs on a chosen GPU) */
+int b200zk_group_peer_access(const b200zk_group *g, int i);  /* 1 when shard i stores its partial directly into the first device */
+int b200zk_multi_bases_upload(b200zk_group *g, int group, const void *points, size_t n, size_t stride, const uint8_t *infinity,
+                              size_t inf_stride, b200zk_group_bases **out);
+int b200zk_multi_bases_precompute(b200zk_group *g, b200zk_group_bases *bases, int window_bits);
+size_t b200zk_multi_bases_len(const b200zk_group_bases *bases);
+void b200zk_multi_bases_free(b200zk_group_bases *bases);
+int b200zk_multi_multiexp(b200zk_group *g, const b200zk_group_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                          const uint8_t *density, uint64_t *out_jacobian);
+/* the future-returning form (up to 4 in flight per group); scalars / density must stay valid until the wait */
+int b200zk_multi_multiexp_async(b200zk_group *g, const b200zk_group_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                                const uint8_t *density, b200zk_group_job **job);
+int b200zk_multi_job_wait(b200zk_group_job *job, uint64_t *out_jacobian);
+/* Host-only helper (needs no device): where a sharded multiexp cuts its exponents.  bounds[0..n_dev] = base-range boundaries of
+ * the shards; e_lo[0..n_dev] receives the exponent split points, local_offset[0..n_dev-1] the base cursor of each shard relative
+ * to its own first base.  The last shard also takes every exponent beyond the end of the bases (it reports UnexpectedEof). */
+int b200zk_multi_plan(const size_t *bounds, int n_dev, size_t base_offset, const uint8_t *density, size_t n_exp, size_t *e_lo,
+                      size_t *local_offset);
 
 /* ---- EvaluationDomain (bellman/src/domain.rs) -------------------------------------------------------------------- */
 /* In-place transform of m = 2^log_m Montgomery Fr coefficients, natural order in and out (domain.rs:83-132).

@@ -496,3 +496,156 @@ def test_two_devices_in_one_process(worker):
         st, want = cref.multiexp("g1", xy, exps[dev])
         want_aff, want_inf = cref.into_affine("g1", want)
         assert st == 0 and bool(got[dev][1][0]) == want_inf and np.array_equal(got[dev][0][0], want_aff)
+
+
+def _devices_for_group(worker, shards):
+    """as many distinct GPUs as the box has, repeating device ids when it has fewer than `shards` (two shards on one GPU run the
+    same code path: own contexts, streams and records; only the NVLink hop is then a local store)"""
+    n = worker.lib.b200zk_device_count()
+    return [d % n for d in range(shards)]
+
+
+@pytest.mark.parametrize("group,shards", [("g1", 2), ("g1", 3), ("g2", 2)])
+def test_one_process_multi_gpu_multiexp(worker, group, shards):
+    """b200zk_init_multi / b200zk_multi_bases_upload / b200zk_multi_multiexp: one host process, bases sharded by contiguous range,
+    exponents cut at the shard boundaries (density-aware), partials summed on the first device == the oracle's unsharded multiexp.
+    Offsets, density maps, precomputed tables, futures in flight, and the Source's error semantics across shards."""
+    import zcash_gpu_thesis_b200 as zk
+
+    code = zk.G1 if group == "g1" else zk.G2
+    r = util.rng(4500 + shards)
+    n = 3001 if group == "g1" else 1201
+    xy, ks = util.random_bases(group, r, n)
+    mw = zk.MultiWorker(_devices_for_group(worker, shards))
+    try:
+        assert len(mw) == shards and all(mw.peer_access(i) in (True, False) for i in range(shards))
+        bases = zk.ShardedBases(mw, code, xy)
+        assert len(bases) == n
+
+        def check(exps, density=None, offset=0):
+            dm = zk.FullDensity() if density is None else zk.DensityTracker(density)
+            got = zk.multiexp(mw, (bases, offset), dm, exps)
+            st, want = cref.multiexp(group, xy, exps, density=density, base_offset=offset)
+            assert st == 0
+            ga, gi = zk.into_affine(worker, code, got)
+            wa, wi = cref.into_affine(group, want)
+            assert bool(gi[0]) == wi and np.array_equal(ga[0], wa)
+
+        exps = util.random_fr_repr(r, n)
+        for rounds in range(2):  # plain windows, then precomputed tables per shard
+            check(exps)
+            check(exps[: n - 700], offset=700)
+            check(exps[:5])                      # everything in the first shard
+            check(exps[:9], offset=n - 9)        # everything in the last shard
+            d = (r.random(n) < 0.55).astype(np.uint8)
+            check(exps, density=d)
+            d2 = (r.random(n) < 0.3).astype(np.uint8)
+            check(exps, density=d2, offset=n // 2)
+            check(exps[:0])
+            bases.precompute(0)
+        # futures in flight (prover.rs:289-318 keeps several)
+        jobs = [util.random_fr_repr(r, n - 10 * t) for t in range(3)]
+        futs = [zk.multiexp_async(mw, (bases, 3 * t), zk.FullDensity(), jobs[t]) for t in range(3)]
+        for t, f in enumerate(futs):
+            st, want = cref.multiexp(group, xy, jobs[t], base_offset=3 * t)
+            ga, gi = zk.into_affine(worker, code, f.wait())
+            wa, wi = cref.into_affine(group, want)
+            assert st == 0 and bool(gi[0]) == wi and np.array_equal(ga[0], wa)
+        # UnexpectedEof: only the last shard can run out of bases, whichever shard the exponents start in
+        with pytest.raises(zk.IoError):
+            zk.multiexp(mw, (bases, 1), zk.FullDensity(), exps)
+        with pytest.raises(zk.IoError):
+            zk.multiexp(mw, (bases, n + 5), zk.FullDensity(), exps[:3])
+        z = exps.copy()
+        z[n - 1] = 0
+        with pytest.raises(zk.IoError):
+            zk.multiexp(mw, (bases, 1), zk.FullDensity(), z)  # the missing base would only have been skipped: still EOF (multiexp.rs:60-62)
+        bases.free()
+        # UnexpectedIdentity in a middle shard fails the whole multiexp; a zero scalar on it does not
+        inf = np.zeros(n, dtype=np.uint8)
+        bad = n // shards + 7
+        inf[bad] = 1
+        ib = zk.ShardedBases(mw, code, xy, inf)
+        with pytest.raises(zk.UnexpectedIdentity):
+            zk.multiexp(mw, (ib, 0), zk.FullDensity(), exps)
+        z = exps.copy()
+        z[bad] = 0
+        got = zk.multiexp(mw, (ib, 0), zk.FullDensity(), z)
+        st, want = cref.multiexp(group, xy, z, inf=inf)
+        assert st == 0 and np.array_equal(zk.into_affine(worker, code, got)[0][0], cref.into_affine(group, want)[0])
+        # which error wins: the first offending exponent in iteration order (identity in shard 1 before the EOF of the last shard)
+        with pytest.raises(zk.UnexpectedIdentity):
+            zk.multiexp(mw, (ib, 1), zk.FullDensity(), exps)
+        ib.free()
+    finally:
+        mw.close()
+
+
+@pytest.mark.parametrize("group", ["g1", "g2"])
+def test_nccl_sharded_multiexp_two_gpus_in_process(worker, group):
+    """The process-per-GPU path without torchrun: two contexts on two GPUs, one host thread each, a communicator from
+    b200zk_nccl_unique_id / b200zk_comm_init, then b200zk_multiexp_sharded_async on the two base-range shards == the oracle on
+    the unsharded input; an identity in ONE shard fails the multiexp on BOTH ranks.  Needs two GPUs (NCCL refuses two ranks on one)."""
+    import ctypes
+    import threading
+
+    import zcash_gpu_thesis_b200 as zk
+    from zcash_gpu_thesis_b200.sharding import shard_density, shard_range
+
+    if worker.lib.b200zk_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    code = zk.G1 if group == "g1" else zk.G2
+    r = util.rng(4600)
+    n = 4000 if group == "g1" else 1500
+    xy, _ = util.random_bases(group, r, n)
+    exps = util.random_fr_repr(r, n)
+    density = (r.random(n) < 0.7).astype(np.uint8)
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[n - 5] = 1  # in rank 1's shard
+    uid = (ctypes.c_uint8 * 128)()
+    assert worker.lib.b200zk_nccl_unique_id(uid) == 0
+    results, errs = [None, None], []
+
+    def run(rank):
+        try:
+            w = zk.Worker(rank)
+            st = w.lib.b200zk_comm_init(w.ctx, uid, rank, 2)
+            assert st == 0, w.last_error()
+            lo, hi = shard_range(n, rank, 2)
+            out = {}
+            for name, dens, use_inf in (("full", None, False), ("dense", density, False), ("identity", None, True)):
+                d_shard, off = shard_density(dens, lo, hi)
+                # the shard owns bases [lo, hi): its cursor starts at off - lo inside its own slice when the density map is full
+                if dens is None:
+                    b = zk.Bases(w, code, xy[lo:hi], inf[lo:hi] if use_inf else None)
+                    local_off = 0
+                else:
+                    b = zk.Bases(w, code, xy)  # density-mapped: every rank keeps the whole vector and starts at its cursor
+                    local_off = off
+                job = ctypes.c_void_p()
+                e = np.ascontiguousarray(exps[lo:hi])
+                st = w.lib.b200zk_multiexp_sharded_async(w.ctx, b.handle, local_off, e.ctypes.data_as(ctypes.c_void_p), hi - lo,
+                                                         None if d_shard is None else np.ascontiguousarray(d_shard).ctypes.data_as(ctypes.c_void_p), ctypes.byref(job))
+                assert st == 0, w.last_error()
+                res = np.zeros(18 if group == "g1" else 36, dtype=np.uint64)
+                out[name] = (w.lib.b200zk_job_wait(job, res.ctypes.data_as(ctypes.c_void_p)), res)
+                b.free()
+            results[rank] = out
+            w.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=run, args=(k,)) for k in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for name, dens in (("full", None), ("dense", density)):
+        st, want = cref.multiexp(group, xy, exps, density=dens)
+        wa, wi = cref.into_affine(group, want)
+        for rank in range(2):
+            code_st, res = results[rank][name]
+            ga, gi = zk.into_affine(worker, code, res)
+            assert code_st == 0 and st == 0 and bool(gi[0]) == wi and np.array_equal(ga[0], wa), (name, rank)
+    assert [results[k]["identity"][0] for k in range(2)] == [zk._lib.ERR_UNEXPECTED_IDENTITY] * 2

@@ -75,3 +75,43 @@ def test_shard_ranges_partition():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
     assert sorted(sum((round_robin(7, r, 3) for r in range(3)), [])) == list(range(7))
+
+
+def test_multi_plan_matches_shard_density():
+    """b200zk_multi_plan (the host logic of the one-process multi-GPU multiexp, callable without a GPU): the exponent cuts and
+    per-shard base cursors give, shard by shard, exactly the (base, exponent) pairs of the unsharded multiexp -- checked by
+    replaying the Source semantics (multiexp.rs:42-68, 174-196) in plain Python."""
+    import zcash_gpu_thesis_b200 as zk
+
+    rng = np.random.default_rng(5)
+
+    def pairs_unsharded(n_bases, off, density, n_exp):
+        out, idx = [], off
+        for i in range(n_exp):
+            if density is not None and not density[i]:
+                continue
+            out.append((i, idx if idx < n_bases else "EOF"))
+            idx += 1
+        return out
+
+    for trial in range(200):
+        nd = int(rng.integers(1, 6))
+        n_bases = int(rng.integers(0, 60))
+        base = n_bases // nd
+        bounds = [d * base + min(d, n_bases % nd) for d in range(nd + 1)]
+        n_exp = int(rng.integers(0, 80))
+        off = int(rng.integers(0, n_bases + 3))
+        density = None if trial % 3 == 0 else (rng.random(n_exp) < rng.random()).astype(np.uint8)
+        e_lo, loc = zk.multi_plan(bounds, off, density, n_exp)
+        assert e_lo[0] == 0 and e_lo[-1] == n_exp and all(e_lo[d] <= e_lo[d + 1] for d in range(nd))
+        got = []
+        for d in range(nd):
+            n_shard = bounds[d + 1] - bounds[d]
+            idx = loc[d]
+            for i in range(e_lo[d], e_lo[d + 1]):
+                if density is not None and not density[i]:
+                    continue
+                got.append((i, bounds[d] + idx if idx < n_shard else "EOF"))
+                idx += 1
+        want = pairs_unsharded(n_bases, off, density, n_exp)
+        assert got == want, (bounds, off, n_exp, None if density is None else density.tolist())

@@ -39,6 +39,9 @@ from .bellman import (  # noqa: F401
     multiexp,
     multiexp_async,
     multiexp_batch,
+    MultiWorker,
+    ShardedBases,
+    multi_plan,
     ntt_host,
     point_op,
 )

@@ -57,6 +57,20 @@ SIGNATURES = {
     "b200zk_nccl_unique_id": (_i, [_vp]),
     "b200zk_comm_init": (_i, [_vp, _vp, _i, _i]),
     "b200zk_allgather_sum_dev": (_i, [_vp, _i, _vp, _vp]),
+    "b200zk_init_multi": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "b200zk_group_destroy": (None, [_vp]),
+    "b200zk_group_last_error": (C.c_char_p, [_vp]),
+    "b200zk_group_size": (_i, [_vp]),
+    "b200zk_group_ctx": (_vp, [_vp, _i]),
+    "b200zk_group_peer_access": (_i, [_vp, _i]),
+    "b200zk_multi_bases_upload": (_i, [_vp, _i, _vp, _sz, _sz, _vp, _sz, C.POINTER(_vp)]),
+    "b200zk_multi_bases_precompute": (_i, [_vp, _vp, _i]),
+    "b200zk_multi_bases_len": (_sz, [_vp]),
+    "b200zk_multi_bases_free": (None, [_vp]),
+    "b200zk_multi_multiexp": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "b200zk_multi_multiexp_async": (_i, [_vp, _vp, _sz, _vp, _sz, _vp, C.POINTER(_vp)]),
+    "b200zk_multi_job_wait": (_i, [_vp, _vp]),
+    "b200zk_multi_plan": (_i, [_vp, _i, _sz, _vp, _sz, _vp, _vp]),
     "b200zk_ntt": (_i, [_vp, _vp, _u32, _i]),
     "b200zk_ntt_dev": (_i, [_vp, _vp, _u32, _i]),
     "b200zk_distribute_powers_dev": (_i, [_vp, _vp, _sz, _vp]),

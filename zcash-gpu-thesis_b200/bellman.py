@@ -338,7 +338,10 @@ def multiexp(pool: Worker, bases, density_map, exponents):
         assert density_map.get_query_size() == n
         density = density_map.as_bytes()
     out = np.zeros(18 if bases.group == L.G1 else 36, dtype=np.uint64)
-    st = pool.lib.b200zk_multiexp(pool.ctx, bases.handle, offset, _ptr(exponents), n, _ptr(density), _ptr(out))
+    if isinstance(pool, MultiWorker):  # one process, several GPUs: `bases` is a ShardedBases
+        st = pool.lib.b200zk_multi_multiexp(pool.handle, bases.handle, offset, _ptr(exponents), n, _ptr(density), _ptr(out))
+    else:
+        st = pool.lib.b200zk_multiexp(pool.ctx, bases.handle, offset, _ptr(exponents), n, _ptr(density), _ptr(out))
     if st:
         _raise(pool, st)
     return out
@@ -410,6 +413,11 @@ def multiexp_async(pool: Worker, bases, density_map, exponents) -> MultiexpFutur
         assert density_map.get_query_size() == n
         density = density_map.as_bytes()
     job = C.c_void_p()
+    if isinstance(pool, MultiWorker):
+        st = pool.lib.b200zk_multi_multiexp_async(pool.handle, bases.handle, offset, _ptr(exponents), n, _ptr(density), C.byref(job))
+        if st:
+            _raise(pool, st)
+        return _GroupFuture(pool, job, bases.group, (exponents, density))
     st = pool.lib.b200zk_multiexp_async(pool.ctx, bases.handle, offset, _ptr(exponents), n, _ptr(density), C.byref(job))
     if st:
         _raise(pool, st)
@@ -427,6 +435,113 @@ def into_affine(pool: Worker, group: int, jacobian):
     if st:
         _raise(pool, st)
     return out, inf
+
+
+# ------------------------------------------------------------------------------------------------------ one process, several GPUs
+class MultiWorker:
+    """A Worker over several GPUs driven by ONE host process (b200zk_init_multi): what the reference's product caller needs, since
+    a single zcashd process issues all the multiexps of a proof (prover.rs:289-318).  `devices` may repeat an id (two shards on
+    one GPU).  `worker(i)` is a plain Worker view of shard i's context (for NTTs or proofs on a chosen GPU)."""
+
+    def __init__(self, devices):
+        self.lib = L.load()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        st = self.lib.b200zk_init_multi(arr, len(self.devices), C.byref(h))
+        if st:
+            raise CudaError(f"b200zk_init_multi({self.devices}) failed with status {st}: no usable CUDA device (there is no CPU fallback)")
+        self.handle = h
+
+    def __len__(self):
+        return len(self.devices)
+
+    def last_error(self):
+        return (self.lib.b200zk_group_last_error(self.handle) or b"").decode()
+
+    def peer_access(self, i):
+        return bool(self.lib.b200zk_group_peer_access(self.handle, i))
+
+    def worker(self, i) -> Worker:
+        w = Worker.__new__(Worker)
+        w.lib, w.device, w._pinned = self.lib, self.devices[i], []
+        w.ctx = C.c_void_p(self.lib.b200zk_group_ctx(self.handle, i))
+        w.close = lambda: None  # owned by the group
+        return w
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.b200zk_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedBases:
+    """A base vector sharded by contiguous range over the GPUs of a MultiWorker (b200zk_multi_bases_upload)."""
+
+    def __init__(self, pool: MultiWorker, group: int, xy, infinity=None):
+        self.worker, self.group = pool, group
+        width = 12 if group == L.G1 else 24
+        xy = _u64(xy, width)
+        self.n = xy.shape[0]
+        inf = None if infinity is None else np.ascontiguousarray(infinity, dtype=np.uint8)
+        h = C.c_void_p()
+        st = pool.lib.b200zk_multi_bases_upload(pool.handle, group, _ptr(xy), self.n, width * 8, _ptr(inf), 1, C.byref(h))
+        if st:
+            _raise(pool, st)
+        self.handle = h
+
+    def __len__(self):
+        return self.n
+
+    def precompute(self, window_bits=0):
+        st = self.worker.lib.b200zk_multi_bases_precompute(self.worker.handle, self.handle, window_bits)
+        if st:
+            _raise(self.worker, st)
+        return self
+
+    def free(self):
+        if getattr(self, "handle", None) is not None and self.worker.handle is not None:
+            self.worker.lib.b200zk_multi_bases_free(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _GroupFuture:
+    def __init__(self, pool, job, group, keep):
+        self.pool, self.job, self.group, self.keep = pool, job, group, keep
+
+    def wait(self):
+        out = np.zeros(18 if self.group == L.G1 else 36, dtype=np.uint64)
+        st = self.pool.lib.b200zk_multi_job_wait(self.job, _ptr(out))
+        self.job, self.keep = None, None
+        if st:
+            _raise(self.pool, st)
+        return out
+
+
+def multi_plan(bounds, base_offset, density, n_exp):
+    """b200zk_multi_plan (host logic only, needs no GPU): exponent split points and per-shard base cursors of a sharded multiexp"""
+    lib = L.load()
+    nd = len(bounds) - 1
+    b = (C.c_size_t * (nd + 1))(*bounds)
+    e_lo = (C.c_size_t * (nd + 1))()
+    off = (C.c_size_t * nd)()
+    d = None if density is None else np.ascontiguousarray(density, dtype=np.uint8)
+    st = lib.b200zk_multi_plan(b, nd, base_offset, _ptr(d), n_exp, e_lo, off)
+    if st:
+        raise ValueError(f"b200zk_multi_plan status {st}")
+    return list(e_lo), list(off)
 
 
 # ------------------------------------------------------------------------------------------------------ domain

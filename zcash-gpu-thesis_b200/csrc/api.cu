@@ -69,11 +69,6 @@ static bool load_nccl(std::string &err) {
 
 using namespace b200zk;
 
-struct b200zk_ctx : public Ctx {};
-struct b200zk_bases : public Bases {};
-struct b200zk_crs : public Crs {};
-struct b200zk_job { b200zk_ctx *ctx; int slot; int group; size_t o_res, o_st; };
-
 namespace b200zk {
 int ctx_lanes(Ctx *ctx, int n) {
     while ((int)ctx->lanes.size() < n) {
@@ -379,6 +374,7 @@ void b200zk_bases_free(b200zk_bases *bases) {
 // ---------------------------------------------------------------------------------------------------------------- multiexp
 int b200zk_set_msm_window(b200zk_ctx *ctx, int window_bits) {
     CHECK_CTX(ctx);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     if (window_bits != 0 && (window_bits < 2 || window_bits > 24)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "window bits must be 0 or in [2, 24]");
     ctx->window_override = window_bits;
     return B200ZK_OK;
@@ -413,6 +409,7 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
                     const uint8_t *density, uint64_t *out_jacobian) {
     CHECK_CTX(ctx);
     if (!bases || !out_jacobian || (n_exp && !scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    if (bases->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bases live on another device");
     USE_DEVICE(ctx);
     const size_t jac_bytes = bases->group == B200ZK_G1 ? 144 : 288;
     // staging: scalars | density | result | status
@@ -434,12 +431,31 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
     return B200ZK_OK;
 }
 
-static int allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total);
+static int status_to_error(b200zk_ctx *ctx, uint32_t status) {
+    if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status, "UnexpectedIdentity: a base at infinity was consumed");
+    if (status == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status, "IoError(UnexpectedEof): expected more bases from source");
+    return B200ZK_OK;
+}
 
-static int multiexp_async_impl(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
-                               const uint8_t *density, b200zk_job **job, bool gather) {
+}  // extern "C"
+
+namespace b200zk {
+static __global__ void k_first_status(const char *__restrict__ recs, size_t n, uint32_t *__restrict__ out) {
+    uint32_t st = 0;
+    for (size_t i = 0; i < n && st == 0; i++) st = *reinterpret_cast<const uint32_t *>(recs + i * REC_BYTES + REC_STATUS);
+    *out = st;
+}
+int first_status(Ctx *ctx, cudaStream_t st, const void *d_records, size_t n, void *d_status_out) {
+    k_first_status<<<1, 1, 0, st>>>((const char *)d_records, n, (uint32_t *)d_status_out);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+int multiexp_enqueue(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp, const uint8_t *density,
+                     void *d_record_out, int *slot_out) {
     CHECK_CTX(ctx);
-    if (!bases || !job || (n_exp && !scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    if (!bases || !slot_out || (n_exp && !scalars)) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    if (bases->ctx->device != ctx->device) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bases live on another device");
     USE_DEVICE(ctx);
     if (!ctx->copy_stream) B200ZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     int si = -1;
@@ -447,7 +463,7 @@ static int multiexp_async_impl(b200zk_ctx *ctx, const b200zk_bases *bases, size_
     if (si < 0) return set_error(ctx, B200ZK_ERR_BAD_ARG, "too many multiexp jobs in flight on this context (max 4): wait for one first");
     Ctx::JobSlot &sl = ctx->slots[si];
     const size_t sc_bytes = n_exp * 32, den_bytes = density ? n_exp : 0;
-    const size_t o_den = (sc_bytes + 255) / 256 * 256, o_res = o_den + (den_bytes + 255) / 256 * 256, o_st = o_res + 512, total = o_st + 256;
+    const size_t o_den = (sc_bytes + 255) / 256 * 256, o_res = o_den + (den_bytes + 255) / 256 * 256, total = o_res + 512;
     if (sl.bytes < total) {
         if (sl.dev) { B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); B200ZK_CUDA(ctx, cudaFree(sl.dev)); sl.dev = nullptr; sl.bytes = 0; }
         B200ZK_CUDA(ctx, cudaMalloc(&sl.dev, total));
@@ -463,18 +479,37 @@ static int multiexp_async_impl(b200zk_ctx *ctx, const b200zk_bases *bases, size_
     if (den_bytes) B200ZK_CUDA(ctx, cudaMemcpyAsync(d + o_den, density, den_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     B200ZK_CUDA(ctx, cudaEventRecord(sl.copied, ctx->copy_stream));
     B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.copied, 0));
-    int rc = msm_run(ctx, bases, base_offset, d, n_exp, density ? (const uint8_t *)(d + o_den) : nullptr, d + o_res, d + o_st, ctx->window_override);
+    char *rec = d_record_out ? (char *)d_record_out : d + o_res;
+    int rc = msm_run(ctx, bases, base_offset, d, n_exp, density ? (const uint8_t *)(d + o_den) : nullptr, rec, rec + REC_STATUS, ctx->window_override);
     if (rc) return rc;
-    const size_t jac_bytes = bases->group == B200ZK_G1 ? 144 : 288;
-    if (gather && ctx->world > 1) {  // this rank's shard partial -> sum over all ranks (NCCL all-gather + adds on the same stream)
-        if ((rc = allgather_sum_dev(ctx, bases->group, d + o_res, d + o_res))) return rc;
-    }
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(sl.host_res, d + o_res, jac_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    B200ZK_CUDA(ctx, cudaMemcpyAsync((char *)sl.host_res + 320, d + o_st, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    B200ZK_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
+    sl.o_res = o_res;
     sl.busy = true;
-    b200zk_job *j = new b200zk_job{ctx, si, bases->group, o_res, o_st};
-    *job = j;
+    *slot_out = si;
+    return B200ZK_OK;
+}
+}  // namespace b200zk
+
+extern "C" {
+
+static int allgather_records(b200zk_ctx *ctx, int group, void *d_record_out);
+
+static int multiexp_async_impl(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
+                               const uint8_t *density, b200zk_job **job, bool gather) {
+    CHECK_CTX(ctx);
+    if (!job) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null argument");
+    USE_DEVICE(ctx);
+    const bool sharded = gather && ctx->world > 1;
+    if (sharded && !ctx->nccl_comm) return set_error(ctx, B200ZK_ERR_NCCL, "communicator not initialised");
+    int si = -1;
+    // sharded: the window-combine kernel writes this rank's record straight into the send slot of the gather buffer
+    int rc = multiexp_enqueue(ctx, bases, base_offset, scalars, n_exp, density, sharded ? ctx->gather_buf : nullptr, &si);
+    if (rc) return rc;
+    Ctx::JobSlot &sl = ctx->slots[si];
+    char *rec = (char *)sl.dev + sl.o_res;
+    if (sharded && (rc = allgather_records(ctx, bases->group, rec))) { sl.busy = false; return rc; }
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(sl.host_res, rec, REC_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaEventRecord(sl.done, ctx->stream));
+    *job = new b200zk_job{ctx, si, bases->group};
     return B200ZK_OK;
 }
 
@@ -492,15 +527,14 @@ int b200zk_job_wait(b200zk_job *job, uint64_t *out_jacobian) {
     b200zk_ctx *ctx = job->ctx;
     Ctx::JobSlot &sl = ctx->slots[job->slot];
     cudaSetDevice(ctx->device);
-    cudaError_t e = cudaEventSynchronize(sl.done);
-    uint32_t status = *(const uint32_t *)((const char *)sl.host_res + 320);
+    cudaError_t e = cudaEventSynchronize(sl.done);  // blocking wait outside the context lock: other threads may submit meanwhile
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
+    uint32_t status = *(const uint32_t *)((const char *)sl.host_res + REC_STATUS);
     if (e == cudaSuccess && out_jacobian) memcpy(out_jacobian, sl.host_res, job->group == B200ZK_G1 ? 144 : 288);
     sl.busy = false;
     delete job;
     if (e != cudaSuccess) return set_error(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e));
-    if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status, "UnexpectedIdentity: a base at infinity was consumed");
-    if (status == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status, "IoError(UnexpectedEof): expected more bases from source");
-    return B200ZK_OK;
+    return status_to_error(ctx, status);
 }
 
 int b200zk_sum_points_dev(b200zk_ctx *ctx, int group, const void *d_points, size_t n, void *d_out) {
@@ -560,25 +594,38 @@ int b200zk_comm_init(b200zk_ctx *ctx, const uint8_t unique_id[128], int rank, in
     if (r != 0) return set_error(ctx, B200ZK_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     ctx->rank = rank;
     ctx->world = world;
-    B200ZK_CUDA(ctx, cudaMalloc(&ctx->gather_buf, (size_t)world * 288));
+    B200ZK_CUDA(ctx, cudaMalloc(&ctx->gather_buf, ((size_t)world + 1) * REC_BYTES));
+    B200ZK_CUDA(ctx, cudaMemset(ctx->gather_buf, 0, ((size_t)world + 1) * REC_BYTES));
     return B200ZK_OK;
+}
+
+// All ranks: send record (gather_buf[0], already written) -> gathered records -> sum of the points and the first non-zero status
+// in rank order (an UnexpectedIdentity / EOF of any shard fails the multiexp on every rank) -> d_record_out.
+static int allgather_records(b200zk_ctx *ctx, int group, void *d_record_out) {
+    char *send = (char *)ctx->gather_buf, *recv = send + REC_BYTES;
+    int r = g_nccl.AllGather(send, recv, REC_BYTES, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream);
+    if (r != 0) return set_error(ctx, B200ZK_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    int rc = msm_sum_points(ctx, group, recv, (size_t)ctx->world, d_record_out, REC_BYTES);
+    if (rc) return rc;
+    return first_status(ctx, ctx->stream, recv, (size_t)ctx->world, (char *)d_record_out + REC_STATUS);
 }
 
 int b200zk_allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total) {
     CHECK_CTX(ctx);
+    if (group != B200ZK_G1 && group != B200ZK_G2) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
     USE_DEVICE(ctx);
-    return allgather_sum_dev(ctx, group, d_partial, d_total);
-}
-static int allgather_sum_dev(b200zk_ctx *ctx, int group, const void *d_partial, void *d_total) {
     const size_t jb = group == B200ZK_G1 ? 144 : 288;
     if (ctx->world == 1 || !ctx->nccl_comm) {
         if (ctx->world != 1) return set_error(ctx, B200ZK_ERR_NCCL, "communicator not initialised");
         if (d_total != d_partial) B200ZK_CUDA(ctx, cudaMemcpyAsync(d_total, d_partial, jb, cudaMemcpyDeviceToDevice, ctx->stream));
         return B200ZK_OK;
     }
-    int r = g_nccl.AllGather(d_partial, ctx->gather_buf, jb, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream);
+    char *send = (char *)ctx->gather_buf, *recv = send + REC_BYTES;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(send, d_partial, jb, cudaMemcpyDeviceToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemsetAsync(send + REC_STATUS, 0, 4, ctx->stream));
+    int r = g_nccl.AllGather(send, recv, REC_BYTES, /* ncclUint8 */ 1, ctx->nccl_comm, ctx->stream);
     if (r != 0) return set_error(ctx, B200ZK_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
-    return msm_sum_points(ctx, group, ctx->gather_buf, (size_t)ctx->world, d_total);
+    return msm_sum_points(ctx, group, recv, (size_t)ctx->world, d_total, REC_BYTES);
 }
 
 // ---------------------------------------------------------------------------------------------------------------- domain
@@ -826,6 +873,7 @@ int b200zk_groth16_prove_batch(b200zk_ctx *ctx, const b200zk_crs *crs, const b20
 
 unsigned long long b200zk_launch_count(b200zk_ctx *ctx, int reset) {
     if (!ctx) return 0;
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     unsigned long long v = ctx->launches;
     if (reset) ctx->launches = 0;
     return v;
@@ -833,6 +881,7 @@ unsigned long long b200zk_launch_count(b200zk_ctx *ctx, int reset) {
 
 int b200zk_profile_enable(b200zk_ctx *ctx, int on) {
     CHECK_CTX(ctx);
+    std::lock_guard<std::recursive_mutex> lock(ctx->mu);
     ctx->prof_on = on != 0;
     return B200ZK_OK;
 }

@@ -55,10 +55,10 @@ struct Ctx {
     // NCCL (loaded lazily, only when a communicator is requested)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
-    void *gather_buf = nullptr;  // world * 288 B
+    void *gather_buf = nullptr;  // (world + 1) records of REC_BYTES: [0] = this rank's send record, [1..] = the gathered ones
     void *small_slot = nullptr;  // 256 B staging for scalar constants
     cudaStream_t copy_stream = nullptr;  // H2D of the next job's exponents while the current one computes
-    struct JobSlot { void *dev = nullptr; size_t bytes = 0; void *host_res = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool busy = false; };
+    struct JobSlot { void *dev = nullptr; size_t bytes = 0, o_res = 0; void *host_res = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool busy = false; };
     JobSlot slots[4];
     int window_override = 0;  // b200zk_set_msm_window
     unsigned long long launches = 0;  // kernels launched by this context (b200zk_launch_count)
@@ -112,7 +112,8 @@ int msm_run(Ctx *ctx, const Bases *bases, size_t base_offset, const void *d_scal
 int msm_fixed_base(Ctx *ctx, int group, const void *d_base_affine, const void *d_scalars, size_t n, uint32_t scalar_bits, void *d_out_affine,
                    uint8_t *d_out_inf);
 int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf);
-int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out);
+// sum of n Jacobian points stored `stride` bytes apart (0 = packed)
+int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out, size_t stride = 0);
 int msm_precompute(Ctx *ctx, Bases *bases, uint32_t c);
 int msm_build_table(Ctx *ctx, int group, const void *d_base_affine, void *d_table, uint32_t nwin);  // 255 * nwin XYZZ entries
 // codec.cu
@@ -140,4 +141,21 @@ int groth16_prove(Ctx *ctx, const Crs *crs, const ProveArgs &args, uint64_t *pro
 int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_t K, uint64_t *proof_a, uint64_t *proof_b, uint64_t *proof_c,
                         uint8_t *inf_flags);
 
+}  // namespace b200zk
+
+// ---- the opaque handle types of the C ABI (defined here so that every translation unit sees one definition)
+struct b200zk_ctx : public b200zk::Ctx {};
+struct b200zk_bases : public b200zk::Bases {};
+struct b200zk_crs : public b200zk::Crs {};
+struct b200zk_job { b200zk_ctx *ctx; int slot; int group; };
+
+namespace b200zk {
+// A partial result travels as one RECORD: the Jacobian point (144 / 288 B) at +0 and the status word at +REC_STATUS.
+static constexpr size_t REC_STATUS = 288, REC_BYTES = 320;
+// Enqueue one multiexp with HOST operands on `ctx` (copy stream -> compute stream) and leave its record in the job slot
+// *slot_out (device: slot.dev + slot.o_res).  d_record_out != nullptr: the window-combine kernel writes the record there instead
+// (a peer pointer: the partial of a shard goes straight into the gather buffer of the combining GPU).  The caller holds no lock.
+int multiexp_enqueue(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp, const uint8_t *density,
+                     void *d_record_out, int *slot_out);
+int first_status(Ctx *ctx, cudaStream_t st, const void *d_records, size_t n, void *d_status_out);  // first non-zero status word, in record order
 }  // namespace b200zk

@@ -7,7 +7,7 @@ namespace b200zk {
     int msm_run_##SUFFIX(Ctx *, const Bases *, size_t, const void *, size_t, const uint8_t *, void *, void *, int, MsmBatch);        \
     int msm_fixed_base_##SUFFIX(Ctx *, const void *, const void *, size_t, uint32_t, void *, uint8_t *);                             \
     int msm_into_affine_##SUFFIX(Ctx *, const void *, size_t, void *, uint8_t *);                                                    \
-    int msm_sum_points_##SUFFIX(Ctx *, const void *, size_t, void *);                                                                \
+    int msm_sum_points_##SUFFIX(Ctx *, const void *, size_t, void *, size_t);                                                              \
     int msm_build_table_##SUFFIX(Ctx *, const void *, void *, uint32_t);                                                             \
     int msm_precompute_##SUFFIX(Ctx *, Bases *, uint32_t);
 DECL(g1)
@@ -29,9 +29,9 @@ int msm_into_affine(Ctx *ctx, int group, const void *d_jac, size_t n, void *d_ou
     if (group == B200ZK_G2) return msm_into_affine_g2(ctx, d_jac, n, d_out_xy, d_out_inf);
     return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
 }
-int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out) {
-    if (group == B200ZK_G1) return msm_sum_points_g1(ctx, d_jac_in, n, d_jac_out);
-    if (group == B200ZK_G2) return msm_sum_points_g2(ctx, d_jac_in, n, d_jac_out);
+int msm_sum_points(Ctx *ctx, int group, const void *d_jac_in, size_t n, void *d_jac_out, size_t stride) {
+    if (group == B200ZK_G1) return msm_sum_points_g1(ctx, d_jac_in, n, d_jac_out, stride);
+    if (group == B200ZK_G2) return msm_sum_points_g2(ctx, d_jac_in, n, d_jac_out, stride);
     return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad group");
 }
 

@@ -774,9 +774,9 @@ __global__ void k_into_affine(const Jacobian<F> *__restrict__ in, size_t n, Affi
 }
 // Sum of n Jacobian points with the reference's add_assign (ec.rs:356-444): strided partials, then a serial fold.
 template <class F>
-__global__ void __launch_bounds__(128) k_sum_points(const Jacobian<F> *__restrict__ in, size_t n, Jacobian<F> *__restrict__ partial, Jacobian<F> *__restrict__ out) {
+__global__ void __launch_bounds__(128) k_sum_points(const char *__restrict__ in, size_t n, size_t stride, Jacobian<F> *__restrict__ partial, Jacobian<F> *__restrict__ out) {
     Jacobian<F> acc = Jacobian<F>::zero();
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) jacobian_add(acc, in[i]);
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) jacobian_add(acc, *reinterpret_cast<const Jacobian<F> *>(in + i * stride));
     partial[threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -793,10 +793,10 @@ static int msm_into_affine_t(Ctx *ctx, const void *d_jac, size_t n, void *d_out_
     return B200ZK_OK;
 }
 template <class F>
-static int msm_sum_points_t(Ctx *ctx, const void *d_jac_in, size_t n, void *d_jac_out) {
+static int msm_sum_points_t(Ctx *ctx, const void *d_jac_in, size_t n, void *d_jac_out, size_t stride) {
     int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, 128 * sizeof(Jacobian<F>));
     if (rc) return rc;
-    k_sum_points<F><<<1, 128, 0, ctx->stream>>>((const Jacobian<F> *)d_jac_in, n, (Jacobian<F> *)ctx->scratch2, (Jacobian<F> *)d_jac_out);
+    k_sum_points<F><<<1, 128, 0, ctx->stream>>>((const char *)d_jac_in, n, stride ? stride : sizeof(Jacobian<F>), (Jacobian<F> *)ctx->scratch2, (Jacobian<F> *)d_jac_out);
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
@@ -813,7 +813,7 @@ static int msm_sum_points_t(Ctx *ctx, const void *d_jac_in, size_t n, void *d_ja
     int msm_into_affine_##SUFFIX(Ctx *ctx, const void *d_jac, size_t n, void *d_out_xy, uint8_t *d_out_inf) {                       \
         return msm_into_affine_t<F>(ctx, d_jac, n, d_out_xy, d_out_inf);                                                           \
     }                                                                                                                              \
-    int msm_sum_points_##SUFFIX(Ctx *ctx, const void *d_jac_in, size_t n, void *d_jac_out) { return msm_sum_points_t<F>(ctx, d_jac_in, n, d_jac_out); } \
+    int msm_sum_points_##SUFFIX(Ctx *ctx, const void *d_jac_in, size_t n, void *d_jac_out, size_t stride) { return msm_sum_points_t<F>(ctx, d_jac_in, n, d_jac_out, stride); } \
     int msm_precompute_##SUFFIX(Ctx *ctx, Bases *bases, uint32_t c) { return msm_precompute_t<F>(ctx, bases, c); }                    \
     int msm_build_table_##SUFFIX(Ctx *ctx, const void *d_base_affine, void *d_table, uint32_t nwin) {                                 \
         k_fixed_base_table<F><<<1, 32, 0, ctx->stream>>>((const Affine<F> *)d_base_affine, (XYZZ<F> *)d_table, nwin);                 \
