@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200zk.so")
+LIB_PATH = os.environ.get("B200ZK_LIB") or os.path.join(_HERE, "libb200zk.so")  # B200ZK_LIB: another build of the same library (A/B measurements)
 
 OK, ERR_UNEXPECTED_IDENTITY, ERR_UNEXPECTED_EOF, ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_NCCL, ERR_DECODE = range(8)
 G1, G2 = 1, 2

@@ -3,6 +3,7 @@
 // EvaluationDomain methods (domain.rs:83-189) and the H block of create_proof (prover.rs:256-287).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 
@@ -111,6 +112,7 @@ int b200zk_init(int device, b200zk_ctx **out) {
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *e = getenv("B200ZK_NTT_LARGE_FROM")) ctx->ntt_large_from = atoi(e);
     *out = ctx;
     return B200ZK_OK;
 }

@@ -29,10 +29,8 @@ struct NttTables {
     uint32_t log_n = 0;
     void *tw = nullptr;        // omega^k,      k < n/2
     void *tw_inv = nullptr;    // omega^-k,     k < n/2
-    void *g_lo = nullptr;      // g^j,          j < 2^LO_BITS
-    void *g_hi = nullptr;      // g^(j << LO_BITS)
-    void *gi_lo = nullptr;     // g^-j
-    void *gi_hi = nullptr;     // g^-(j << LO_BITS) * n^-1
+    void *g_pow = nullptr;     // g^i,          i < n   (coset_fft pre-scale; built on first use)
+    void *gi_pow = nullptr;    // g^-i / n,     i < n   (icoset_fft post-scale)
     void *consts = nullptr;    // fr_t[8]: omega, omega_inv, n_inv, g, g_inv, z_inv (1/(g^n - 1)), ...
 };
 
@@ -61,6 +59,7 @@ struct Ctx {
     struct JobSlot { void *dev = nullptr; size_t bytes = 0, o_res = 0; void *host_res = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool busy = false; };
     JobSlot slots[4];
     int window_override = 0;  // b200zk_set_msm_window
+    int ntt_large_from = 22;  // log2 size from which a transform uses the eight-elements-per-thread kernels (B200ZK_NTT_LARGE_FROM)
     unsigned long long launches = 0;  // kernels launched by this context (b200zk_launch_count)
     bool prof_on = false;        // bracket the dominant MSM kernel with events
     // lanes: child contexts on the same device (own stream + workspaces) on which one create_proof runs its independent

@@ -15,11 +15,7 @@
 
 namespace b200zk {
 
-static constexpr uint32_t LO_BITS = 12;  // two-level g^i table: g^i = lo[i & 4095] * hi[i >> 12]
-static constexpr int NTT_THREADS = 128;
-static constexpr uint32_t MAX_TILE_LOG = 10;
-
-enum { C_OMEGA = 0, C_OMEGA_INV = 1, C_N_INV = 2, C_G = 3, C_G_INV = 4, C_Z_INV = 5, C_G_STEP = 6, C_GI_STEP = 7, C_COUNT = 8 };
+enum { C_OMEGA = 0, C_OMEGA_INV = 1, C_N_INV = 2, C_G = 3, C_G_INV = 4, C_Z_INV = 5, C_COUNT = 8 };
 
 // fr.rs:50-55 ROOT_OF_UNITY and fr.rs:38-44 GENERATOR (=7), Montgomery limbs
 __device__ __constant__ uint32_t FR_ROOT_OF_UNITY[8] = {0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u, 0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau};
@@ -43,8 +39,6 @@ __global__ void k_ntt_setup(fr_t *consts, uint32_t log_n) {
     consts[C_G] = g;
     consts[C_G_INV] = g_inv;
     consts[C_Z_INV] = (g.pow(nn) - fr_t::one()).inverse();
-    consts[C_G_STEP] = g.pow(1ull << LO_BITS);
-    consts[C_GI_STEP] = g_inv.pow(1ull << LO_BITS);
 }
 
 // out[k] = base^k * (scale ? *scale : 1), k < count; 16 consecutive powers per thread
@@ -60,95 +54,194 @@ __global__ void k_pow_table(fr_t *__restrict__ out, const fr_t *__restrict__ bas
     }
 }
 
+// ------------------------------------------------------------------------------------------------ the pass kernel
+// One pass = B consecutive radix-2 DIT stages (bits [s0, s0 + B) of the element index) over tiles of 2^B coupled elements x 2^Q
+// independent columns.  A thread owns EIGHT elements in registers and runs up to three stages on them without touching shared
+// memory (a radix-8 butterfly network: 12 butterflies, 7 distinct twiddles); between such rounds the tile is regrouped through
+// shared memory.  Per pass of 8 stages that is 2 shared-memory round trips and 2 barriers instead of 8 + 8, and the first
+// round reads its elements straight from HBM / the last one writes them straight back.  Twiddles omega^k come from the
+// per-domain table (precomputed once): a round's addresses only depend on the thread, so they are prefetched into L1 before the
+// data arrives and each butterfly's twiddle load is an L1 hit.  The butterfly itself (t = hi * w; hi = lo - t; lo += t,
+// domain.rs:300-308) is one out-of-line body shared by all call sites (instruction-cache friendly, see fp.cuh).
+//   FIRST pass: input gathered in bit-reversed order (domain.rs:286-295 folded into the loads: the columns are the TOP index
+//   bits, so the four columns of a tile are four ADJACENT source elements = one 128-byte line) and the twiddles of its first
+//   round are 1, omega^(n/4), omega^(n/8) ...: the products by 1 are skipped (x * 1 = x exactly, the output stays bit-identical).
+//   coset_fft / icoset_fft / ifft scalings: ONE product per element at the first load (g^i table) / the last store
+//   (g^-i / n table or the constant 1 / n).
 struct NttPass {
-    uint32_t log_n, s0, B, q;
-    int bitrev_load;  // gather in[bitrev(g)] (first pass)
-    int pre_scale;    // multiply loaded element i by lo[i & mask] * hi[i >> LO_BITS]   (coset_fft: g^i)
-    int post_scale;   // 1: multiply stored element by consts[C_N_INV] (ifft); 2: by lo*hi tables (icoset_fft: g^-i / n)
+    const fr_t *in;
+    fr_t *out;
+    const fr_t *tw;       // omega^k (or omega^-k), k < n / 2
+    const fr_t *scale;    // pre_scale: g^i, i < n;  post_scale == 2: g^-i / n, i < n;  post_scale == 1: &n^-1
+    uint32_t log_n, s0;
+    int pre_scale, post_scale;
 };
 
-// Tile layout in shared memory: two planes of 16-byte halves (limbs 0-3 of every element, then limbs 4-7).  Consecutive
-// threads touch consecutive 16-byte words of a plane, so an element moves with 2 conflict-free LDS.128 / STS.128 -- the
-// kernel is bound by instruction issue as much as by the multiplier (one butterfly = 114 wide multiplies x 4 issue
-// cycles against ~450 instructions), and the limb-major layout used before cost 32 LDS/STS.32 per butterfly instead of 8.
-#ifdef B200ZK_NTT_LIMB_MAJOR
-__device__ __forceinline__ fr_t sm_load(const uint32_t *sm, uint32_t tile, uint32_t e) {
-    fr_t x;
-#pragma unroll
-    for (int l = 0; l < 8; l++) x.v[l] = sm[l * tile + e];
-    return x;
+struct FrPair { fr_t lo, hi; };
+// The product inside is the fused operand-scanning Montgomery product of fp.cuh.  Measured alternatives at 2^24 (ms per fft):
+// this 3.92; everything inlined (no call, 170 KB of straight-line code per kernel) 4.28; schoolbook rows + separate reduction
+// 4.30; one-level Karatsuba (48 instead of 64 wide multiplies) 5.04; 12 instead of 16 resident warps (no spills) 4.02.
+static __device__ __noinline__ FrPair ntt_bfly_call(fr_t lo, fr_t hi, fr_t w) {
+    const fr_t t = fr_t::mul_inline(hi, w);
+    return {lo + t, lo - t};
 }
-__device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t tile, uint32_t e, const fr_t &x) {
-#pragma unroll
-    for (int l = 0; l < 8; l++) sm[l * tile + e] = x.v[l];
-}
-#else
-__device__ __forceinline__ fr_t sm_load(const uint32_t *sm, uint32_t tile, uint32_t e) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(sm);
-    const uint4 lo = p[e], hi = p[tile + e];
+static __device__ __noinline__ fr_t ntt_mul_call(fr_t a, fr_t b) { return fr_t::mul_inline(a, b); }
+
+// shared-memory tile: two planes of 16-byte halves, XOR-swizzled so that the 8 lanes of a quarter warp always hit 8 different
+// 16-byte bank groups whatever bit positions the round's register-resident index bits occupy
+__device__ __forceinline__ uint32_t ntt_swz(uint32_t e) { return e ^ ((e >> 3) & 7u); }
+template <int TILE>
+__device__ __forceinline__ fr_t ntt_sm_load(const uint4 *sm, uint32_t e) {
+    const uint32_t w = ntt_swz(e);
+    const uint4 lo = sm[w], hi = sm[TILE + w];
     fr_t x;
     x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w;
     x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
     return x;
 }
-__device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t tile, uint32_t e, const fr_t &x) {
-    uint4 *p = reinterpret_cast<uint4 *>(sm);
-    p[e] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-    p[tile + e] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+template <int TILE>
+__device__ __forceinline__ void ntt_sm_store(uint4 *sm, uint32_t e, const fr_t &x) {
+    const uint32_t w = ntt_swz(e);
+    sm[w] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    sm[TILE + w] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
-#endif
+__device__ __forceinline__ void ntt_prefetch(const fr_t *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-#ifndef B200ZK_NTT_UNROLL
-#define B200ZK_NTT_UNROLL 1  // 2 and 4 measured no faster (3.86 / 3.88 / 3.88 ms at 2^24)
-#endif
-// CB / CQ: the pass shape as compile-time constants (0 = take it from `p`): the 2^24 transform runs three (8, 2) passes,
-// and with constant shifts the index arithmetic of a butterfly shrinks (the kernel is issue-bound, see sm_load).
-template <int CB, int CQ>
-__global__ void __launch_bounds__(NTT_THREADS, 7) k_ntt_pass(const fr_t *__restrict__ in, fr_t *__restrict__ out, const fr_t *__restrict__ tw,
-                                                         const fr_t *__restrict__ sc_lo, const fr_t *__restrict__ sc_hi,
-                                                         const fr_t *__restrict__ consts, NttPass p) {
-    extern __shared__ __align__(16) uint32_t sm[];
-    if (CB) { p.B = CB; p.q = CQ; }
-    constexpr int UNROLL = CB ? B200ZK_NTT_UNROLL : 1;  // butterflies of one stage unrolled per thread (specialised shapes)
-    const uint32_t T = p.B + p.q, TILE = 1u << T;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t vshift = p.s0 == 0 ? 0 : p.q;
-    const uint32_t midbits = p.s0 == 0 ? 0 : p.s0 - p.q;
-    const uint32_t mid = tile & ((1u << midbits) - 1), high = tile >> midbits;
-    auto gidx = [&](uint32_t e) -> uint32_t {
-        if (p.s0 == 0) return (tile << T) | e;
-        uint32_t u = e & ((1u << p.q) - 1), v = e >> p.q;
-        return (high << (p.s0 + p.B)) | (v << p.s0) | (mid << p.q) | u;
-    };
-    for (uint32_t e = threadIdx.x; e < TILE; e += NTT_THREADS) {
-        uint32_t g = gidx(e);
-        uint32_t src = p.bitrev_load ? (__brev(g) >> (32 - p.log_n)) : g;
-        fr_t x = in[src];
-        if (p.pre_scale) x = (x * sc_lo[src & ((1u << LO_BITS) - 1)]) * sc_hi[src >> LO_BITS];
-        sm_store(sm, TILE, e, x);
-    }
-    __syncthreads();
-    for (uint32_t k = 0; k < p.B; k++) {
-        const uint32_t s = p.s0 + k, bitpos = k + vshift;
-#pragma unroll(UNROLL)
-        for (uint32_t bf = threadIdx.x; bf < TILE / 2; bf += NTT_THREADS) {
-            uint32_t lo = ((bf >> bitpos) << (bitpos + 1)) | (bf & ((1u << bitpos) - 1));
-            uint32_t hi = lo | (1u << bitpos);
-            uint32_t j = gidx(lo) & ((1u << s) - 1);
-            fr_t w = tw[(size_t)j << (p.log_n - 1 - s)];
-            fr_t a = sm_load(sm, TILE, lo);
-            fr_t t = sm_load(sm, TILE, hi) * w;
-            sm_store(sm, TILE, lo, a + t);
-            sm_store(sm, TILE, hi, a - t);
+// K stages on the E = 2^XB register-resident elements x[0..E): x's index bit i is the i-th of the round's stage bits.
+// idx0 = the table index of the first stage's twiddle; stage j, butterfly with low index bits xl = xi & (2^j - 1):
+// twiddle index = (idx0 >> j) + (xl << (log_n - 1 - j)).  TRIVIAL: idx0 = 0 (first round of the first pass), so the butterflies
+// with xl = 0 multiply by omega^0 = 1 and skip the product.
+// the twiddle addresses of a round only depend on the thread: requested into L1 before the round's data is touched
+template <int K, bool TRIVIAL>
+__device__ __forceinline__ void ntt_round_prefetch(const fr_t *__restrict__ tw, uint32_t idx0, uint32_t log_n) {
+#pragma unroll
+    for (int j = 0; j < K; j++)
+#pragma unroll
+        for (int xl = TRIVIAL ? 1 : 0; xl < (1 << j); xl++) ntt_prefetch(tw + ((idx0 >> j) + ((uint32_t)xl << (log_n - 1 - j))));
+}
+template <int XB, int K, bool TRIVIAL>
+__device__ __forceinline__ void ntt_round(fr_t (&x)[1 << XB], const fr_t *__restrict__ tw, uint32_t idx0, uint32_t log_n) {
+    constexpr int E = 1 << XB;
+    if (XB > 1) ntt_round_prefetch<K, TRIVIAL>(tw, idx0, log_n);  // measured: prefetching every round's twiddles at kernel start is slower
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        fr_t w0;
+        if (j == 0 && !TRIVIAL) w0 = tw[idx0];
+#pragma unroll
+        for (int xi = 0; xi < E; xi++) {
+            if (xi & (1 << j)) continue;
+            const int xl = xi & ((1 << j) - 1), hi = xi | (1 << j);
+            if (TRIVIAL && xl == 0) {  // w = 1
+                const fr_t a = x[xi], b = x[hi];
+                x[xi] = a + b;
+                x[hi] = a - b;
+            } else {
+                const fr_t w = j == 0 ? w0 : tw[(idx0 >> j) + ((uint32_t)xl << (log_n - 1 - j))];
+                const FrPair r = ntt_bfly_call(x[xi], x[hi], w);
+                x[xi] = r.lo;
+                x[hi] = r.hi;
+            }
         }
-        __syncthreads();
     }
-    for (uint32_t e = threadIdx.x; e < TILE; e += NTT_THREADS) {
-        uint32_t g = gidx(e);
-        fr_t x = sm_load(sm, TILE, e);
-        if (p.post_scale == 1) x = x * consts[C_N_INV];
-        else if (p.post_scale == 2) x = (x * sc_lo[g & ((1u << LO_BITS) - 1)]) * sc_hi[g >> LO_BITS];
-        out[g] = x;
+}
+
+// XB = 3 (eight elements per thread) for large transforms; XB = 1 (one butterfly per thread and stage, a shared-memory exchange
+// after every stage) for small ones, whose time is the length of the serial chain of a thread, not the work
+template <int B, int Q, int XB>
+struct NttShape {
+    static constexpr int T = B + Q, TILE = 1 << T, THREADS = 1 << (T - XB);
+    static constexpr int K0 = (B - 1) % XB + 1, ROUNDS = (B + XB - 1) / XB;  // the short round comes first: rounds of K0, XB, XB ... stages
+    static constexpr int WARPS = XB == 3 ? 16 : 32;  // resident warps per SM the register budget is set for (16 -> 128 registers)
+    static constexpr int MINBLOCKS = (WARPS * 32 / THREADS) < 1 ? 1 : (WARPS * 32 / THREADS);
+    static constexpr size_t SMEM = ROUNDS > 1 ? (size_t)2 * TILE * sizeof(uint4) : 0;
+};
+
+template <int B, int Q, int XB, bool FIRST>
+__global__ void __launch_bounds__(NttShape<B, Q, XB>::THREADS, NttShape<B, Q, XB>::MINBLOCKS) k_ntt_pass(NttPass p) {
+    typedef NttShape<B, Q, XB> S;
+    constexpr int E = 1 << XB;
+    extern __shared__ __align__(16) uint4 ntt_sm[];
+    const uint32_t t = threadIdx.x, tile = blockIdx.x;
+    const uint32_t log_n = p.log_n, s0 = FIRST ? 0u : p.s0;
+    // tile-local element e = (v << Q) | col  ->  global index
+    //   FIRST:  g = col << (log_n - Q) | tile << B | v      (columns = top bits: adjacent after the bit reversal)
+    //   else:   g = high << (s0 + B) | v << s0 | mid << Q | col,  tile = high << (s0 - Q) | mid
+    const uint32_t mid = FIRST ? 0u : tile & ((1u << (s0 - Q)) - 1u), high = FIRST ? 0u : tile >> (s0 - Q);
+    auto gidx = [&](uint32_t e) -> uint32_t {
+        const uint32_t v = e >> Q, col = e & ((1u << Q) - 1u);
+        if (FIRST) return (Q ? col << (log_n - Q) : 0u) | (tile << B) | v;
+        return (high << (s0 + B)) | (v << s0) | (mid << Q) | col;
+    };
+    // twiddle base index of a round's first stage: (g mod 2^(s0 + b)) << (log_n - 1 - s0 - b), b = the round's first stage bit
+    auto round_idx0 = [&](int P) -> uint32_t {
+        const uint32_t e0 = ((t >> P) << (P + XB)) | (t & ((1u << P) - 1u));
+        const uint32_t sb = s0 + (uint32_t)(P - Q);
+        return sb == 0 ? 0u : (gidx(e0) & ((1u << sb) - 1u)) << (log_n - 1 - sb);
+    };
+    fr_t x[E];
+#pragma unroll
+    for (int r = 0; r < S::ROUNDS; r++) {
+        const int P = (r == 0 ? 0 : S::K0 + XB * (r - 1)) + Q;  // position of the XB register-resident bits inside e
+        const uint32_t e0 = ((t >> P) << (P + XB)) | (t & ((1u << P) - 1u));
+        const uint32_t idx0 = round_idx0(P);
+        if (r == 0) {
+#pragma unroll
+            for (int xi = 0; xi < E; xi++) {
+                const uint32_t g = gidx(e0 | ((uint32_t)xi << P));
+                const uint32_t src = FIRST ? __brev(g) >> (32 - log_n) : g;
+                x[xi] = p.in[src];
+                if (FIRST && p.pre_scale) x[xi] = ntt_mul_call(x[xi], p.scale[src]);
+            }
+        } else {
+            __syncthreads();
+#pragma unroll
+            for (int xi = 0; xi < E; xi++) x[xi] = ntt_sm_load<S::TILE>(ntt_sm, e0 | ((uint32_t)xi << P));
+        }
+        if (r == 0) {
+            if (S::K0 == 1) ntt_round<XB, 1, FIRST>(x, p.tw, idx0, log_n);
+            else if (S::K0 == 2) ntt_round<XB, 2, FIRST>(x, p.tw, idx0, log_n);
+            else ntt_round<XB, 3, FIRST>(x, p.tw, idx0, log_n);
+        } else {
+            ntt_round<XB, XB, false>(x, p.tw, idx0, log_n);
+        }
+        if (r == S::ROUNDS - 1) {
+#pragma unroll
+            for (int xi = 0; xi < E; xi++) {
+                const uint32_t g = gidx(e0 | ((uint32_t)xi << P));
+                if (p.post_scale == 1) x[xi] = ntt_mul_call(x[xi], p.scale[0]);
+                else if (p.post_scale == 2) x[xi] = ntt_mul_call(x[xi], p.scale[g]);
+                p.out[g] = x[xi];
+            }
+        } else {
+#pragma unroll
+            for (int xi = 0; xi < E; xi++) ntt_sm_store<S::TILE>(ntt_sm, e0 | ((uint32_t)xi << P), x[xi]);
+        }
+    }
+}
+
+// n <= 4: one thread, the reference's loop as is (bit reversal, log n stages; domain.rs:272-315) with the scalings around it
+__global__ void k_ntt_tiny(fr_t *a, const fr_t *tw, const fr_t *g_pow, const fr_t *gi_pow, const fr_t *consts, uint32_t log_n, int kind) {
+    const uint32_t n = 1u << log_n;
+    fr_t x[4];
+    for (uint32_t i = 0; i < n; i++) {
+        x[i] = a[i];
+        if (kind == B200ZK_COSET_FFT) x[i] = x[i] * g_pow[i];
+    }
+    if (log_n == 2) { fr_t t = x[1]; x[1] = x[2]; x[2] = t; }  // bit reversal of 2-bit indices
+    for (uint32_t s = 0; s < log_n; s++) {
+        const uint32_t m = 1u << s;
+        for (uint32_t k = 0; k < n; k += 2 * m)
+            for (uint32_t j = 0; j < m; j++) {
+                fr_t t = x[k + j + m] * tw[(size_t)j << (log_n - 1 - s)];
+                fr_t lo = x[k + j];
+                x[k + j + m] = lo - t;
+                x[k + j] = lo + t;
+            }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        if (kind == B200ZK_IFFT) x[i] = x[i] * consts[C_N_INV];
+        else if (kind == B200ZK_ICOSET_FFT) x[i] = x[i] * gi_pow[i];
+        a[i] = x[i];
     }
 }
 
@@ -191,7 +284,7 @@ __global__ void k_domain_z(const fr_t *tau, uint32_t log_m, fr_t *out) {
 }
 
 static void free_tables(NttTables &t) {
-    cudaFree(t.tw); cudaFree(t.tw_inv); cudaFree(t.g_lo); cudaFree(t.g_hi); cudaFree(t.gi_lo); cudaFree(t.gi_hi); cudaFree(t.consts);
+    cudaFree(t.tw); cudaFree(t.tw_inv); cudaFree(t.g_pow); cudaFree(t.gi_pow); cudaFree(t.consts);
     t = NttTables();
 }
 
@@ -202,34 +295,63 @@ int ntt_get_tables(Ctx *ctx, uint32_t log_n, NttTables **out) {
     t.log_n = log_n;
     const size_t n = (size_t)1 << log_n;
     const size_t half = n > 1 ? n / 2 : 1;
-    const size_t lo_cnt = (size_t)1 << LO_BITS;
-    const size_t hi_cnt = (n >> LO_BITS) ? (n >> LO_BITS) : 1;
     B200ZK_CUDA(ctx, cudaMalloc(&t.consts, C_COUNT * sizeof(fr_t)));
     B200ZK_CUDA(ctx, cudaMalloc(&t.tw, half * sizeof(fr_t)));
     B200ZK_CUDA(ctx, cudaMalloc(&t.tw_inv, half * sizeof(fr_t)));
-    B200ZK_CUDA(ctx, cudaMalloc(&t.g_lo, lo_cnt * sizeof(fr_t)));
-    B200ZK_CUDA(ctx, cudaMalloc(&t.gi_lo, lo_cnt * sizeof(fr_t)));
-    B200ZK_CUDA(ctx, cudaMalloc(&t.g_hi, hi_cnt * sizeof(fr_t)));
-    B200ZK_CUDA(ctx, cudaMalloc(&t.gi_hi, hi_cnt * sizeof(fr_t)));
     fr_t *c = (fr_t *)t.consts;
     k_ntt_setup<<<1, 1, 0, ctx->stream>>>(c, log_n);
     auto blocks = [](size_t cnt) { return (unsigned)((cnt + 16 * 128 - 1) / (16 * 128)); };
     k_pow_table<<<blocks(half), 128, 0, ctx->stream>>>((fr_t *)t.tw, c + C_OMEGA, nullptr, half);
     k_pow_table<<<blocks(half), 128, 0, ctx->stream>>>((fr_t *)t.tw_inv, c + C_OMEGA_INV, nullptr, half);
-    k_pow_table<<<blocks(lo_cnt), 128, 0, ctx->stream>>>((fr_t *)t.g_lo, c + C_G, nullptr, lo_cnt);
-    k_pow_table<<<blocks(lo_cnt), 128, 0, ctx->stream>>>((fr_t *)t.gi_lo, c + C_G_INV, nullptr, lo_cnt);
-    k_pow_table<<<blocks(hi_cnt), 128, 0, ctx->stream>>>((fr_t *)t.g_hi, c + C_G_STEP, nullptr, hi_cnt);
-    k_pow_table<<<blocks(hi_cnt), 128, 0, ctx->stream>>>((fr_t *)t.gi_hi, c + C_GI_STEP, c + C_N_INV, hi_cnt);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { free_tables(t); return set_error(ctx, B200ZK_ERR_CUDA, cudaGetErrorString(e)); }
     auto ins = ctx->ntt_tables.emplace(log_n, t);
     *out = &ins.first->second;
     return B200ZK_OK;
 }
+// the coset tables g^i and g^-i / n (n entries each, natural order), built on the first coset transform of a domain size
+static int ntt_coset_tables(Ctx *ctx, NttTables *t) {
+    if (t->g_pow) return B200ZK_OK;
+    const size_t n = (size_t)1 << t->log_n;
+    B200ZK_CUDA(ctx, cudaMalloc(&t->g_pow, n * sizeof(fr_t)));
+    B200ZK_CUDA(ctx, cudaMalloc(&t->gi_pow, n * sizeof(fr_t)));
+    fr_t *c = (fr_t *)t->consts;
+    const unsigned blocks = (unsigned)((n + 16 * 128 - 1) / (16 * 128));
+    k_pow_table<<<blocks, 128, 0, ctx->stream>>>((fr_t *)t->g_pow, c + C_G, nullptr, n);
+    k_pow_table<<<blocks, 128, 0, ctx->stream>>>((fr_t *)t->gi_pow, c + C_G_INV, c + C_N_INV, n);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
 
 void ntt_free_all_tables(Ctx *ctx) {
     for (auto &kv : ctx->ntt_tables) free_tables(kv.second);
     ctx->ntt_tables.clear();
+}
+
+template <int B, int Q, int XB, bool FIRST>
+static int ntt_launch(Ctx *ctx, const NttPass &p) {
+    typedef NttShape<B, Q, XB> S;
+    static bool opted_in[64] = {};  // per device: dynamic shared memory above 48 KiB needs the opt-in
+    if (S::SMEM > 48 * 1024 && ctx->device < 64 && !opted_in[ctx->device]) {
+        B200ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass<B, Q, XB, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        opted_in[ctx->device] = true;
+    }
+    const unsigned tiles = (unsigned)(((size_t)1 << p.log_n) >> S::T);
+    k_ntt_pass<B, Q, XB, FIRST><<<tiles, S::THREADS, S::SMEM, ctx->stream>>>(p);
+    ctx->launches++;
+    return B200ZK_OK;
+}
+template <bool FIRST>
+static int ntt_dispatch(Ctx *ctx, const NttPass &p, uint32_t B, uint32_t Q, uint32_t XB) {
+#define B200ZK_NTT_CASE(CB, CQ, CX) if (B == CB && Q == CQ && XB == CX) return ntt_launch<CB, CQ, CX, FIRST>(ctx, p);
+    // large transforms: eight elements per thread, four columns
+    B200ZK_NTT_CASE(6, 2, 3) B200ZK_NTT_CASE(7, 2, 3) B200ZK_NTT_CASE(8, 2, 3) B200ZK_NTT_CASE(9, 2, 3)
+    // small transforms: two elements per thread
+    B200ZK_NTT_CASE(5, 2, 1) B200ZK_NTT_CASE(6, 2, 1) B200ZK_NTT_CASE(7, 2, 1) B200ZK_NTT_CASE(8, 2, 1)
+    B200ZK_NTT_CASE(5, 0, 1) B200ZK_NTT_CASE(6, 0, 1) B200ZK_NTT_CASE(7, 0, 1) B200ZK_NTT_CASE(8, 0, 1) B200ZK_NTT_CASE(9, 0, 1)
+    if (FIRST) { B200ZK_NTT_CASE(3, 0, 1) B200ZK_NTT_CASE(4, 0, 1) }
+#undef B200ZK_NTT_CASE
+    return set_error(ctx, B200ZK_ERR_BAD_ARG, "internal: no NTT kernel for this pass shape");
 }
 
 int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
@@ -240,41 +362,49 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
     NttTables *t;
     int st = ntt_get_tables(ctx, log_n, &t);
     if (st) return st;
+    const bool coset = kind == B200ZK_COSET_FFT || kind == B200ZK_ICOSET_FFT;
+    if (coset && (st = ntt_coset_tables(ctx, t))) return st;
     const size_t n = (size_t)1 << log_n;
-    st = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, n * sizeof(fr_t));
-    if (st) return st;
-    fr_t *A = (fr_t *)d_coeffs, *S = (fr_t *)ctx->scratch;
+    fr_t *A = (fr_t *)d_coeffs;
     const bool inverse = kind == B200ZK_IFFT || kind == B200ZK_ICOSET_FFT;
     const fr_t *tw = (const fr_t *)(inverse ? t->tw_inv : t->tw);
-
-    uint32_t npass = log_n <= MAX_TILE_LOG ? 1 : (log_n + 7) / 8;
-    uint32_t base = log_n / npass, extra = log_n % npass;
+    if (log_n <= 2) {
+        k_ntt_tiny<<<1, 1, 0, ctx->stream>>>(A, tw, (const fr_t *)t->g_pow, (const fr_t *)t->gi_pow, (const fr_t *)t->consts, log_n, kind);
+        ctx->launches++;
+        B200ZK_CUDA(ctx, cudaGetLastError());
+        return B200ZK_OK;
+    }
+    // Large transforms (work-bound): passes of at most 9 stages, eight elements per thread, four adjacent columns per tile
+    // (128-byte runs in HBM).  Small ones (latency-bound: the time is the serial chain of one thread): the same passes
+    // with one butterfly per thread and stage, columns only while they leave two tiles per SM.
+    const bool large = log_n >= (uint32_t)ctx->ntt_large_from;
+    const uint32_t npass = (log_n + 8) / 9;
+    st = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, n * sizeof(fr_t));
+    if (st) return st;
+    fr_t *S = (fr_t *)ctx->scratch;
+    const uint32_t base = log_n / npass, extra = log_n % npass;
     uint32_t s0 = 0;
+    const fr_t *src = A;
     for (uint32_t ps = 0; ps < npass; ps++) {
         NttPass p;
+        const uint32_t B = base + (ps < extra ? 1 : 0);
+        uint32_t Q = npass == 1 ? 0 : 2;
+        if (!large && Q && ((n >> (B + Q)) < (size_t)2 * ctx->sm_count || B + Q > 10)) Q = 0;
         p.log_n = log_n;
         p.s0 = s0;
-        p.B = base + (ps < extra ? 1 : 0);
-        p.q = npass == 1 ? 0 : (MAX_TILE_LOG - p.B < 2 ? MAX_TILE_LOG - p.B : 2);
-        while (p.q > 0 && (n >> (p.B + p.q)) < (size_t)2 * ctx->sm_count) p.q--;  // small transforms: more, narrower tiles to fill the SMs
-        p.bitrev_load = ps == 0;
+        p.tw = tw;
         p.pre_scale = (ps == 0 && kind == B200ZK_COSET_FFT) ? 1 : 0;
         p.post_scale = ps + 1 == npass ? (kind == B200ZK_IFFT ? 1 : kind == B200ZK_ICOSET_FFT ? 2 : 0) : 0;
-        const fr_t *lo = (const fr_t *)(p.pre_scale ? t->g_lo : t->gi_lo), *hi = (const fr_t *)(p.pre_scale ? t->g_hi : t->gi_hi);
-        const fr_t *src = ps == 0 ? A : S;
-        fr_t *dst = (ps + 1 == npass && npass > 1) ? A : S;
-        uint32_t T = p.B + p.q;
-        size_t smem = (size_t)8 * sizeof(uint32_t) << T;
-        unsigned tiles = (unsigned)(n >> T);
-#define B200ZK_NTT_SHAPE(CB, CQ) \
-    if (p.B == CB && p.q == CQ) k_ntt_pass<CB, CQ><<<tiles, NTT_THREADS, smem, ctx->stream>>>(src, dst, tw, lo, hi, (const fr_t *)t->consts, p); else
-        B200ZK_NTT_SHAPE(8, 2) B200ZK_NTT_SHAPE(7, 2) B200ZK_NTT_SHAPE(6, 2) B200ZK_NTT_SHAPE(5, 2)
-        k_ntt_pass<0, 0><<<tiles, NTT_THREADS, smem, ctx->stream>>>(src, dst, tw, lo, hi, (const fr_t *)t->consts, p);
-#undef B200ZK_NTT_SHAPE
-        ctx->launches++;
-        s0 += p.B;
+        p.scale = p.pre_scale ? (const fr_t *)t->g_pow : p.post_scale == 2 ? (const fr_t *)t->gi_pow : (const fr_t *)t->consts + C_N_INV;
+        p.in = src;
+        fr_t *dst = src == A ? S : A;  // a pass reads one buffer and writes the other (a tile's outputs are not its inputs)
+        p.out = dst;
+        st = ps == 0 ? ntt_dispatch<true>(ctx, p, B, Q, large ? 3 : 1) : ntt_dispatch<false>(ctx, p, B, Q, large ? 3 : 1);
+        if (st) return st;
+        src = dst;
+        s0 += B;
     }
-    if (npass == 1) B200ZK_CUDA(ctx, cudaMemcpyAsync(A, S, n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (src != A) B200ZK_CUDA(ctx, cudaMemcpyAsync(A, src, n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
