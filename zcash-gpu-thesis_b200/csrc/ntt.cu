@@ -145,8 +145,9 @@ __device__ __forceinline__ void ntt_round(fr_t (&x)[1 << XB], const fr_t *__rest
     }
 }
 
-// XB = 3 (eight elements per thread) for large transforms; XB = 1 (one butterfly per thread and stage, a shared-memory exchange
-// after every stage) for small ones, whose time is the length of the serial chain of a thread, not the work
+// XB = 3 (eight elements per thread) for large transforms; XB = 1 (one butterfly per thread and stage; the elements change hands
+// by warp shuffle while the partner is a lane of the same warp, through shared memory afterwards) for small ones, whose time
+// is the length of the serial chain of a thread, not the work
 template <int B, int Q, int XB>
 struct NttShape {
     static constexpr int T = B + Q, TILE = 1 << T, THREADS = 1 << (T - XB);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(NttShape<B, Q, XB>::THREADS, NttShape<B, Q, XB
                 x[xi] = p.in[src];
                 if (FIRST && p.pre_scale) x[xi] = ntt_mul_call(x[xi], p.scale[src]);
             }
-        } else {
+        } else if (!(XB == 1 && P - 1 < 5)) {  // (otherwise the previous round handed its elements over by warp shuffle)
             __syncthreads();
 #pragma unroll
             for (int xi = 0; xi < E; xi++) x[xi] = ntt_sm_load<S::TILE>(ntt_sm, e0 | ((uint32_t)xi << P));
@@ -212,6 +213,16 @@ __global__ void __launch_bounds__(NttShape<B, Q, XB>::THREADS, NttShape<B, Q, XB
                 else if (p.post_scale == 2) x[xi] = ntt_mul_call(x[xi], p.scale[g]);
                 p.out[g] = x[xi];
             }
+        } else if (XB == 1 && P < 5) {
+            // Warp-shuffle butterfly exchange.  The next stage pairs elements whose index differs in the bit this thread's id holds
+            // at position P, and its partner there is lane ^ (1 << P) of the same warp: each of the two keeps the element whose
+            // stage bit equals its own id bit and swaps the other one -- no shared memory, no barrier.
+            const bool up = (t >> P) & 1u;
+            const fr_t send = up ? x[0] : x[E - 1];
+            fr_t recv;
+#pragma unroll
+            for (int l = 0; l < 8; l++) recv.v[l] = __shfl_xor_sync(0xffffffffu, send.v[l], 1u << P);
+            if (up) x[0] = recv; else x[E - 1] = recv;
         } else {
 #pragma unroll
             for (int xi = 0; xi < E; xi++) ntt_sm_store<S::TILE>(ntt_sm, e0 | ((uint32_t)xi << P), x[xi]);
