@@ -203,6 +203,11 @@ int b200zk_multi_multiexp(b200zk_group *g, const b200zk_group_bases *bases, size
 int b200zk_multi_multiexp_async(b200zk_group *g, const b200zk_group_bases *bases, size_t base_offset, const uint64_t *scalars, size_t n_exp,
                                 const uint8_t *density, b200zk_group_job **job);
 int b200zk_multi_job_wait(b200zk_group_job *job, uint64_t *out_jacobian);
+/* The H block of create_proof (prover.rs:256-287) over the group: a, b and c are independent until the pointwise a * b - c
+ * (the reference runs them as three scoped tasks, prover.rs:257-266), so each is uploaded to and transformed on its own GPU
+ * (ifft + coset_fft, round-robin over the group); b and c then cross to the first device peer to peer and it finishes.  Same
+ * arguments and result as b200zk_h_poly.  Pays off for large domains (Sprout's m = 2^21); at 2^17 one GPU is as fast. */
+int b200zk_multi_h_poly(b200zk_group *g, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_m, uint64_t *out);
 /* Host-only helper (needs no device): where a sharded multiexp cuts its exponents.  bounds[0..n_dev] = base-range boundaries of
  * the shards; e_lo[0..n_dev] receives the exponent split points, local_offset[0..n_dev-1] the base cursor of each shard relative
  * to its own first base.  The last shard also takes every exponent beyond the end of the bases (it reports UnexpectedEof). */

@@ -153,3 +153,26 @@ def test_h_poly_matches_oracle(worker, n):
     want = cref.h_poly(pad(a), pad(b), pad(c))
     got = zk.h_poly(worker, a, b, c)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,shards", [(1, 3), (1000, 3), (98785, 3), (98785, 2), (5000, 1)])
+def test_h_poly_over_a_group_of_gpus(worker, n, shards):
+    """b200zk_multi_h_poly: a, b, c transformed on separate GPUs of a one-process group (prover.rs:257-266 runs them as three
+    scoped tasks), b and c copied peer to peer to the first device for the pointwise combine == the oracle's H coefficients.
+    With fewer GPUs than shards the device ids repeat (separate contexts and streams on one GPU: the same code path)."""
+    import zcash_gpu_thesis_b200 as zk
+
+    r = util.rng(600 + n + shards)
+    a, b, c = (util.random_fr_mont(r, n) for _ in range(3))
+    m = 1
+    while m < n:
+        m *= 2
+    pad = lambda v: np.concatenate([v, np.zeros((m - n, 4), dtype=np.uint64)])
+    want = cref.h_poly(pad(a), pad(b), pad(c))
+    ndev = worker.lib.b200zk_device_count()
+    mw = zk.MultiWorker([d % ndev for d in range(shards)])
+    try:
+        assert np.array_equal(zk.h_poly(mw, a, b, c), want)
+        assert np.array_equal(zk.h_poly(mw, a, b, c), want)  # workspaces reused
+    finally:
+        mw.close()

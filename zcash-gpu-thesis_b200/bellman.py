@@ -642,7 +642,10 @@ def h_poly(worker: Worker, a, b, c):
         return p
 
     out = np.zeros((max(m - 1, 0), 4), dtype=np.uint64)
-    st = worker.lib.b200zk_h_poly(worker.ctx, _ptr(pad(a)), _ptr(pad(b)), _ptr(pad(c)), exp, _ptr(out))
+    if isinstance(worker, MultiWorker):  # a, b, c on three GPUs, peer-to-peer combine on the first (b200zk_multi_h_poly)
+        st = worker.lib.b200zk_multi_h_poly(worker.handle, _ptr(pad(a)), _ptr(pad(b)), _ptr(pad(c)), exp, _ptr(out))
+    else:
+        st = worker.lib.b200zk_h_poly(worker.ctx, _ptr(pad(a)), _ptr(pad(b)), _ptr(pad(c)), exp, _ptr(out))
     if st:
         _raise(worker, st)
     return out

@@ -267,4 +267,60 @@ int b200zk_multi_multiexp(b200zk_group *g, const b200zk_group_bases *gb, size_t 
     return b200zk_multi_job_wait(job, out_jacobian);
 }
 
+// The H block of create_proof (prover.rs:256-287) over the group's GPUs: the a, b and c vectors are independent until the
+// pointwise a * b - c (prover.rs:257-266 runs them as three scoped tasks), so each goes to its own GPU (round-robin over the
+// group), is transformed there (ifft + coset_fft), and b, c are then copied peer to peer (NVLink) into the first device, which
+// finishes (combine, divide by z, icoset_fft, into_repr).  Worth it for large domains (2 x m x 32 B cross the link once).
+int b200zk_multi_h_poly(b200zk_group *g, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_m, uint64_t *out) {
+    if (!g) return B200ZK_ERR_BAD_ARG;
+    if (!a || !b || !c || !out) return gerr(g, B200ZK_ERR_BAD_ARG, "null argument");
+    if (log_m >= 32) return gerr(g, B200ZK_ERR_DEGREE_TOO_LARGE, "log_m >= Fr::S (32)");
+    std::lock_guard<std::mutex> lock(g->mu);
+    const int nd = (int)g->ctxs.size();
+    const size_t bytes = ((size_t)1 << log_m) * 32;
+    const uint64_t *src[3] = {a, b, c};
+    b200zk_ctx *owner[3] = {g->ctxs[0], g->ctxs[1 % nd], g->ctxs[2 % nd]};
+    b200zk_ctx *c0 = g->ctxs[0];
+    // device 0 workspace: a | b | c | out (its own vectors are transformed in place there); other owners: one vector each
+    {
+        std::lock_guard<std::recursive_mutex> l0(c0->mu);
+        G_CUDA(g, cudaSetDevice(c0->device));
+        int rc = ensure_scratch(c0, &c0->scratch3, &c0->scratch3_bytes, 4 * bytes);
+        if (rc) return gerr(g, rc, c0->last_error);
+    }
+    char *w0 = (char *)c0->scratch3;
+    void *where[3];
+    for (int i = 0; i < 3; i++) {
+        b200zk_ctx *cx = owner[i];
+        std::lock_guard<std::recursive_mutex> lx(cx->mu);
+        G_CUDA(g, cudaSetDevice(cx->device));
+        if (cx == c0) {
+            where[i] = w0 + (size_t)i * bytes;
+        } else {
+            // two of the three vectors may share a context when the group has two GPUs: slot i of that context's workspace
+            int rc = ensure_scratch(cx, &cx->scratch3, &cx->scratch3_bytes, 3 * bytes);
+            if (rc) return gerr(g, rc, cx->last_error);
+            where[i] = (char *)cx->scratch3 + (size_t)i * bytes;
+        }
+        G_CUDA(g, cudaMemcpyAsync(where[i], src[i], bytes, cudaMemcpyHostToDevice, cx->stream));
+        int rc = ntt_h_poly_front(cx, where[i], log_m);
+        if (rc) return gerr(g, rc, cx->last_error);
+        if (cx != c0) {  // hand the transformed vector to the first device over the peer link, on the owner's stream
+            G_CUDA(g, cudaMemcpyPeerAsync(w0 + (size_t)i * bytes, c0->device, where[i], cx->device, bytes, cx->stream));
+            G_CUDA(g, cudaEventRecord(cx->ev_join, cx->stream));
+        }
+    }
+    std::lock_guard<std::recursive_mutex> l0(c0->mu);
+    G_CUDA(g, cudaSetDevice(c0->device));
+    for (int i = 1; i < 3; i++)
+        if (owner[i] != c0) G_CUDA(g, cudaStreamWaitEvent(c0->stream, owner[i]->ev_join, 0));
+    int rc = ntt_h_poly_tail(c0, w0, w0 + bytes, w0 + 2 * bytes, log_m, w0 + 3 * bytes);
+    if (rc) return gerr(g, rc, c0->last_error);
+    if (bytes > 32) G_CUDA(g, cudaMemcpyAsync(out, w0 + 3 * bytes, bytes - 32, cudaMemcpyDeviceToHost, c0->stream));
+    G_CUDA(g, cudaStreamSynchronize(c0->stream));
+    for (int i = 1; i < 3; i++)
+        if (owner[i] != c0) { cudaSetDevice(owner[i]->device); G_CUDA(g, cudaStreamSynchronize(owner[i]->stream)); }
+    return B200ZK_OK;
+}
+
 }  // extern "C"

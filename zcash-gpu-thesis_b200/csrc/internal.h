@@ -98,6 +98,8 @@ void ntt_free_all_tables(Ctx *ctx);
 int ntt_divide_by_z_on_coset(Ctx *ctx, void *d_coeffs, uint32_t log_n);
 int ntt_domain_z(Ctx *ctx, const void *d_tau, uint32_t log_n, void *d_out);
 int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *d_out_repr);
+int ntt_h_poly_front(Ctx *ctx, void *d_v, uint32_t log_n);  // ifft + coset_fft of one of a, b, c (prover.rs:257-265)
+int ntt_h_poly_tail(Ctx *ctx, void *d_a, const void *d_b, const void *d_c, uint32_t log_n, void *d_out_repr);  // prover.rs:267-287
 // msm.cu
 // A batch of K multiexps over the SAME bases (K proofs over one CRS): exponent vector k starts k * scalar_stride exponents
 // after the first, its density map k * density_stride bytes after the first; the K multiexps are separate bucket sets of one

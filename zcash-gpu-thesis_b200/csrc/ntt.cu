@@ -443,14 +443,16 @@ int ntt_domain_z(Ctx *ctx, const void *d_tau, uint32_t log_n, void *d_out) {
     return B200ZK_OK;
 }
 
-int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *d_out_repr) {
+// prover.rs:257-265 for ONE of the three vectors: ifft, then coset_fft
+int ntt_h_poly_front(Ctx *ctx, void *d_v, uint32_t log_n) {
+    int st;
+    if ((st = ntt_run(ctx, d_v, log_n, B200ZK_IFFT))) return st;
+    return ntt_run(ctx, d_v, log_n, B200ZK_COSET_FFT);
+}
+// prover.rs:267-287 once a, b, c are on the coset: a = (a * b - c) / z(g), icoset_fft, into_repr of the first m - 1 coefficients
+int ntt_h_poly_tail(Ctx *ctx, void *d_a, const void *d_b, const void *d_c, uint32_t log_n, void *d_out_repr) {
     int st;
     const size_t n = (size_t)1 << log_n;
-    void *v[3] = {d_a, d_b, d_c};
-    for (int i = 0; i < 3; i++) {
-        if ((st = ntt_run(ctx, v[i], log_n, B200ZK_IFFT))) return st;
-        if ((st = ntt_run(ctx, v[i], log_n, B200ZK_COSET_FFT))) return st;
-    }
     NttTables *t;
     if ((st = ntt_get_tables(ctx, log_n, &t))) return st;
     ctx->launches += 2;
@@ -459,6 +461,14 @@ int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *
     if (n > 1) k_into_repr<<<(unsigned)((n - 1 + 255) / 256), 256, 0, ctx->stream>>>((const fr_t *)d_a, (fr_t *)d_out_repr, n - 1);
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
+}
+
+int ntt_h_poly(Ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n, void *d_out_repr) {
+    int st;
+    void *v[3] = {d_a, d_b, d_c};
+    for (int i = 0; i < 3; i++)
+        if ((st = ntt_h_poly_front(ctx, v[i], log_n))) return st;
+    return ntt_h_poly_tail(ctx, d_a, d_b, d_c, log_n, d_out_repr);
 }
 
 }  // namespace b200zk
