@@ -252,6 +252,21 @@ int b200zk_crs_create(b200zk_ctx *ctx, const b200zk_bases *h, const b200zk_bases
                       const b200zk_bases *b_g2, const uint64_t alpha_g1[12], const uint64_t beta_g1[12], const uint64_t beta_g2[24],
                       const uint64_t delta_g1[12], const uint64_t delta_g2[24], const uint8_t *vk_infinity, b200zk_crs **out);
 void b200zk_crs_free(b200zk_crs *crs);
+/* Parameters::read (groth16/mod.rs:287-382; VerifyingKey::read :160-212): the whole proving key from its wire format -- vk
+ * (alpha_g1, beta_g1, beta_g2, gamma_g2, delta_g1, delta_g2, u32 count + ic), then h, l, a, b_g1, b_g2 each as a big-endian u32
+ * count + uncompressed points.  The vk points are always fully checked (into_affine) and may be the identity; ic and the query
+ * vectors may not ("point at infinity"); `checked` selects into_affine / into_affine_unchecked for the query vectors.  Points are
+ * decoded on the device and stay resident; the CRS owns them (freed by b200zk_crs_free).  Bad or truncated input ->
+ * B200ZK_ERR_DECODE with the reason in b200zk_last_error. */
+int b200zk_parameters_read(b200zk_ctx *ctx, const uint8_t *bytes, size_t len, int checked, b200zk_crs **out);
+/* Parameters::write (groth16/mod.rs:252-285) of a CRS made by b200zk_parameters_read: byte-identical to what was read. */
+size_t b200zk_parameters_size(const b200zk_crs *crs);
+int b200zk_parameters_write(b200zk_ctx *ctx, const b200zk_crs *crs, uint8_t *out, size_t cap);
+/* The VerifyingKey of such a CRS: 108 words (alpha_g1 | beta_g1 | beta_g2 | gamma_g2 | delta_g1 | delta_g2, affine Montgomery),
+ * six infinity flags and ic (12 words per element; pass ic = NULL to query the count first). */
+int b200zk_crs_verifying_key(const b200zk_crs *crs, uint64_t vk[108], uint8_t vk_inf[6], uint64_t *ic, size_t *n_ic);
+int b200zk_crs_query_sizes(const b200zk_crs *crs, size_t sizes[5]);            /* lengths of h, l, a, b_g1, b_g2 */
+int b200zk_crs_precompute(b200zk_ctx *ctx, b200zk_crs *crs, int window_bits);  /* b200zk_bases_precompute on every query vector */
 /* create_proof for an already synthesized ProvingAssignment (prover.rs:84-190): a, b, c = the evaluation vectors
  * (n_constraints x 4 u64 Montgomery, including the `x * 0 = 0` input rows of prover.rs:228-234); inputs / aux = the
  * assignments as canonical FrRepr (prover.rs:290-291); the three density maps as bytes; r, s canonical FrRepr.
@@ -280,6 +295,12 @@ typedef struct b200zk_prove_input {
 int b200zk_groth16_prove_batch(b200zk_ctx *ctx, const b200zk_crs *crs, const b200zk_prove_input *proofs, size_t n_proofs, size_t n_constraints,
                                size_t n_inputs, size_t n_aux, int lockstep, uint64_t *proofs_a, uint64_t *proofs_b, uint64_t *proofs_c,
                                uint8_t *inf_flags);
+
+/* The batch as the outer FFI of the reference sees it: librustzcash_sapling_spend_proof (librustzcash/src/rustzcash.rs:1375-1626)
+ * ends in create_random_proof + Proof::write into a 192-byte buffer (rustzcash.rs:1556-1601).  N assignments in, N x 192 proof
+ * bytes out (a | b | c compressed, groth16/mod.rs:43-53), encoded on the device. */
+int b200zk_groth16_prove_batch_bytes(b200zk_ctx *ctx, const b200zk_crs *crs, const b200zk_prove_input *proofs, size_t n_proofs, size_t n_constraints,
+                                     size_t n_inputs, size_t n_aux, int lockstep, uint8_t *out_proofs);
 
 /* Per-kernel timing for the roofline report: when enabled, b200zk_multiexp(_dev) brackets its dominant kernel
  * (bucket accumulation) with CUDA events on the context's stream; read() synchronises and returns the summed

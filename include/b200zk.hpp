@@ -177,7 +177,11 @@ private:
 };
 
 // groth16::Parameters resident in HBM (groth16/mod.rs:215-238) = the ParameterSource of create_proof
-struct VerifyingKeyPoints { G1Affine alpha_g1, beta_g1, delta_g1; G2Affine beta_g2, delta_g2; };
+struct VerifyingKeyPoints {
+    G1Affine alpha_g1, beta_g1, delta_g1;
+    G2Affine beta_g2, delta_g2;
+    std::array<uint8_t, 5> infinity{};  // the `infinity` flags of alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2 (delta at infinity -> UnexpectedIdentity, prover.rs:320-324)
+};
 class Parameters {
 public:
     Parameters(const Worker &w, const std::vector<G1Affine> &h, const std::vector<G1Affine> &l, const std::vector<G1Affine> &a,
@@ -185,7 +189,7 @@ public:
         : h_(w, h), l_(w, l), a_(w, a), b1_(w, b_g1), b2_(w, b_g2) {
         if (precompute) { h_.precompute(); l_.precompute(); a_.precompute(); b1_.precompute(); b2_.precompute(); }
         w.check(b200zk_crs_create(w.ctx(), h_.handle(), l_.handle(), a_.handle(), b1_.handle(), b2_.handle(), vk.alpha_g1.data(), vk.beta_g1.data(),
-                                  vk.beta_g2.data(), vk.delta_g1.data(), vk.delta_g2.data(), nullptr, &crs_));
+                                  vk.beta_g2.data(), vk.delta_g1.data(), vk.delta_g2.data(), vk.infinity.data(), &crs_));
     }
     ~Parameters() { b200zk_crs_free(crs_); }
     Parameters(const Parameters &) = delete;
@@ -208,6 +212,10 @@ struct ProvingAssignment {
 
 // groth16::create_proof after circuit synthesis (prover.rs:249-364)
 inline Proof create_proof(const Worker &w, const Parameters &params, const ProvingAssignment &p, const FrRepr &r, const FrRepr &s) {
+    if (p.a.empty() || p.b.size() != p.a.size() || p.c.size() != p.a.size() || p.input_assignment.empty() ||
+        p.a_aux_density.bv.size() != p.aux_assignment.size() || p.b_aux_density.bv.size() != p.aux_assignment.size() ||
+        p.b_input_density.bv.size() != p.input_assignment.size())
+        throw std::invalid_argument("ProvingAssignment: a, b, c need one evaluation per constraint and the density maps one entry per variable");
     Proof out{};
     w.check(b200zk_groth16_prove(w.ctx(), params.handle(), p.a[0].data(), p.b[0].data(), p.c[0].data(), p.a.size(), p.input_assignment[0].data(),
                                  p.input_assignment.size(), p.aux_assignment.empty() ? nullptr : p.aux_assignment[0].data(), p.aux_assignment.size(),

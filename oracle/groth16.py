@@ -294,3 +294,25 @@ def proof_bytes(proof):
     """Proof::write, groth16/mod.rs:43-53: 48 + 96 + 48 compressed bytes (BLS12-381 only)."""
     from .curve import G1, G2
     return G1.encode_compressed(proof.a) + G2.encode_compressed(proof.b) + G1.encode_compressed(proof.c)
+
+
+def verifying_key_bytes(vk):
+    """VerifyingKey::write, groth16/mod.rs:140-158 (BLS12-381 only): six uncompressed points, u32 BE count, ic"""
+    from .curve import G1, G2
+    out = G1.encode_uncompressed(vk.alpha_g1) + G1.encode_uncompressed(vk.beta_g1) + G2.encode_uncompressed(vk.beta_g2)
+    out += G2.encode_uncompressed(vk.gamma_g2) + G1.encode_uncompressed(vk.delta_g1) + G2.encode_uncompressed(vk.delta_g2)
+    out += len(vk.ic).to_bytes(4, "big")
+    for p in vk.ic:
+        out += G1.encode_uncompressed(p)
+    return out
+
+
+def parameters_bytes(params):
+    """Parameters::write, groth16/mod.rs:252-285: vk, then h, l, a, b_g1 (G1) and b_g2 (G2), each a u32 BE count + uncompressed points"""
+    from .curve import G1, G2
+    out = verifying_key_bytes(params.vk)
+    for G, v in ((G1, params.h), (G1, params.l), (G1, params.a), (G1, params.b_g1), (G2, params.b_g2)):
+        out += len(v).to_bytes(4, "big")
+        for p in v:
+            out += G.encode_uncompressed(p)
+    return out

@@ -142,6 +142,8 @@ def test_batched_proofs_equal_single_proofs(worker):
         assert got.write(worker) == proof_bytes(want)
     one = zk.create_proof_from_assignment(worker, dev, *batch[3])
     assert one.write(worker) == proofs[3].write(worker)
+    # the outer-FFI form: N assignments in, N x 192 bytes out (b200zk_groth16_prove_batch_bytes)
+    assert zk.create_proof_bytes_from_assignments(worker, dev, batch, lockstep=2) == [proof_bytes(w_) for w_ in wants]
     assert zk.create_proofs_from_assignments(worker, dev, []) == []
     with pytest.raises(ValueError):
         zk.create_proofs_from_assignments(worker, dev, [batch[0], tuple(x[:-1] for x in batch[1][:3]) + batch[1][3:]])  # fewer constraints
@@ -271,3 +273,73 @@ def test_spend_shaped_proof_matches_oracle(worker, precompute):
         wants.append(spend.assemble(crs, answers[k % 3], r, s))
     proofs = zk.create_proofs_from_assignments(worker, params, batch, lockstep=8)
     assert [p.write(worker) for p in proofs] == wants
+
+
+def test_parameters_read_write_round_trip(worker):
+    """groth16/mod.rs:536-545 (serialization test of the reference) re-targeted: Parameters::write bytes made by the oracle ->
+    Parameters::read on the device (checked and unchecked) -> the proofs equal the oracle's, Parameters::write gives the same bytes
+    back, the VerifyingKey comes back element by element; truncated input, a point at infinity in a query vector and (checked) a
+    point off the curve are decoding errors."""
+    import zcash_gpu_thesis_b200 as zk
+    from oracle.groth16 import parameters_bytes
+
+    E = BlsEngine
+    r0 = util.rng(2500)
+    rnd = lambda: util.rows_to_ints(util.random_fr_repr(r0, 1))[0]
+    consts = [rnd() for _ in range(6)]
+    params, _ = generate_parameters(E, MiMCLike(0, 0, consts), G1.gen, G2.gen, *[rnd() for _ in range(5)])
+    data = parameters_bytes(params)
+    asg = synthesize_assignment(E, MiMCLike(rnd(), rnd(), consts))
+    r, s = rnd(), rnd()
+    want = proof_bytes(prove_from_assignment(E, asg, params, r, s))
+    for checked in (True, False):
+        for pre in (False, True):
+            dev = zk.Parameters.read(worker, data, checked=checked, precompute=pre)
+            assert dev.query_sizes() == dict(h=len(params.h), l=len(params.l), a=len(params.a), b_g1=len(params.b_g1), b_g2=len(params.b_g2))
+            assert _gpu_prove(worker, dev, asg, r, s).write(worker) == want
+            assert dev.write() == data
+            vk = dev.verifying_key()
+            assert list(map(int, vk["gamma_g2"][0])) == G2.affine_to_limbs(params.vk.gamma_g2) and not vk["gamma_g2"][1]
+            assert [list(map(int, row)) for row in vk["ic"]] == [G1.affine_to_limbs(p) for p in params.vk.ic]
+            dev.free()
+    for cut in (10, 96 * 3 + 192 * 3 + 2, len(data) - 1):
+        with pytest.raises(zk.GroupDecodingError):
+            zk.Parameters.read(worker, data[:cut])
+    # a point at infinity inside the h vector (flag byte 0x40, all else zero): rejected even when unchecked (mod.rs:300-304)
+    h_off = 96 * 3 + 192 * 3 + 4 + 96 * len(params.vk.ic) + 4
+    bad = bytearray(data)
+    bad[h_off:h_off + 96] = bytes([0x40]) + bytes(95)
+    with pytest.raises(zk.GroupDecodingError):
+        zk.Parameters.read(worker, bytes(bad), checked=False)
+    # a coordinate changed: off the curve -> only the checked read notices
+    bad = bytearray(data)
+    bad[h_off + 95] ^= 1
+    with pytest.raises(zk.GroupDecodingError):
+        zk.Parameters.read(worker, bytes(bad), checked=True)
+    zk.Parameters.read(worker, bytes(bad), checked=False).free()
+    # parameters assembled from separate vectors carry no gamma_g2 / ic: write refuses
+    with pytest.raises(ValueError):
+        _upload(worker, params).write()
+
+
+def test_identity_vk_elements_are_skipped(worker):
+    """add_assign_mixed skips an identity operand (ec.rs:447-449): alpha_g1 / beta_g1 / beta_g2 at infinity must not be added
+    as finite points by the assembly (prover.rs:326-345).  Oracle: the same parameters with those elements at infinity."""
+    import zcash_gpu_thesis_b200 as zk
+
+    E = BlsEngine
+    r0 = util.rng(2600)
+    rnd = lambda: util.rows_to_ints(util.random_fr_repr(r0, 1))[0]
+    consts = [rnd() for _ in range(4)]
+    params, _ = generate_parameters(E, MiMCLike(0, 0, consts), G1.gen, G2.gen, *[rnd() for _ in range(5)])
+    params.vk.alpha_g1 = G1.affine_zero()
+    params.vk.beta_g1 = G1.affine_zero()
+    params.vk.beta_g2 = G2.affine_zero()
+    pack = lambda G, v: np.array([G.affine_to_limbs(p) for p in v], dtype=np.uint64).reshape(len(v), -1)
+    vk = params.vk
+    zero1, zero2 = np.zeros(12, np.uint64), np.zeros(24, np.uint64)
+    dev = zk.Parameters(worker, pack(G1, params.h), pack(G1, params.l), pack(G1, params.a), pack(G1, params.b_g1), pack(G2, params.b_g2),
+                        zero1, zero1, zero2, _aff_limbs(G1, vk.delta_g1), _aff_limbs(G2, vk.delta_g2), vk_infinity=[1, 1, 1, 0, 0])
+    asg = synthesize_assignment(E, MiMCLike(rnd(), rnd(), consts))
+    r, s = rnd(), rnd()
+    assert _gpu_prove(worker, dev, asg, r, s).write(worker) == proof_bytes(prove_from_assignment(E, asg, params, r, s))

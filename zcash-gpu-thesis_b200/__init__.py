@@ -24,6 +24,7 @@ from .bellman import (  # noqa: F401
     Worker,
     create_proof_from_assignment,
     create_proofs_from_assignments,
+    create_proof_bytes_from_assignments,
     create_proof,
     create_random_proof,
     create_proofs,

@@ -86,8 +86,15 @@ SIGNATURES = {
     "b200zk_h_poly_dev": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),
     "b200zk_crs_create": (_i, [_vp] * 12 + [C.POINTER(_vp)]),
     "b200zk_crs_free": (None, [_vp]),
+    "b200zk_parameters_read": (_i, [_vp, _vp, _sz, _i, C.POINTER(_vp)]),
+    "b200zk_parameters_size": (_sz, [_vp]),
+    "b200zk_parameters_write": (_i, [_vp, _vp, _vp, _sz]),
+    "b200zk_crs_verifying_key": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_sz)]),
+    "b200zk_crs_query_sizes": (_i, [_vp, _vp]),
+    "b200zk_crs_precompute": (_i, [_vp, _vp, _i]),
     "b200zk_groth16_prove": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200zk_groth16_prove_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
+    "b200zk_groth16_prove_batch_bytes": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _i, _vp]),
     "b200zk_launch_count": (C.c_ulonglong, [_vp, _i]),
     "b200zk_profile_enable": (_i, [_vp, _i]),
     "b200zk_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),

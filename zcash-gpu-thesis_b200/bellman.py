@@ -759,6 +759,60 @@ class Parameters:
             _raise(worker, st)
         self.handle = hnd
 
+    @classmethod
+    def read(cls, worker, data: bytes, checked: bool = False, precompute: bool = True):
+        """Parameters::read (groth16/mod.rs:287-382): the proving key from its wire format, decoded on the device and kept
+        resident.  `checked` = into_affine (curve + subgroup tests) for the query vectors; the vk is always checked.
+        Raises GroupDecodingError for malformed or truncated input and for a point at infinity in ic / a query vector."""
+        self = cls.__new__(cls)
+        self.worker = worker
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        hnd = C.c_void_p()
+        st = worker.lib.b200zk_parameters_read(worker.ctx, _ptr(buf), buf.shape[0], int(checked), C.byref(hnd))
+        if st:
+            _raise(worker, st)
+        self.handle = hnd
+        self.h = self.l = self.a = self.b_g1 = self.b_g2 = None  # owned by the CRS object
+        if precompute:
+            st = worker.lib.b200zk_crs_precompute(worker.ctx, hnd, 0)
+            if st:
+                _raise(worker, st)
+        return self
+
+    def write(self) -> bytes:
+        """Parameters::write (groth16/mod.rs:252-285); only for parameters that came from `read` (they carry gamma_g2 and ic)."""
+        size = self.worker.lib.b200zk_parameters_size(self.handle)
+        if size == 0:
+            raise ValueError("these parameters were not made by Parameters.read: gamma_g2 and ic are unknown")
+        out = np.zeros(size, dtype=np.uint8)
+        st = self.worker.lib.b200zk_parameters_write(self.worker.ctx, self.handle, _ptr(out), size)
+        if st:
+            _raise(self.worker, st)
+        return out.tobytes()
+
+    def query_sizes(self):
+        sizes = (C.c_size_t * 5)()
+        st = self.worker.lib.b200zk_crs_query_sizes(self.handle, sizes)
+        if st:
+            _raise(self.worker, st)
+        return dict(zip(("h", "l", "a", "b_g1", "b_g2"), (int(v) for v in sizes)))
+
+    def verifying_key(self):
+        """groth16::VerifyingKey (mod.rs:100-126) as Montgomery limb arrays: dict with alpha_g1, beta_g1, beta_g2, gamma_g2,
+        delta_g1, delta_g2 (each (xy, infinity)) and ic (n, 12)"""
+        vk = np.zeros(108, dtype=np.uint64)
+        inf = np.zeros(6, dtype=np.uint8)
+        n = C.c_size_t()
+        st = self.worker.lib.b200zk_crs_verifying_key(self.handle, _ptr(vk), _ptr(inf), None, C.byref(n))
+        if st:
+            raise ValueError("these parameters carry no full VerifyingKey (not made by Parameters.read)")
+        ic = np.zeros((n.value, 12), dtype=np.uint64)
+        self.worker.lib.b200zk_crs_verifying_key(self.handle, None, None, _ptr(ic), C.byref(n))
+        off = dict(alpha_g1=(0, 12), beta_g1=(12, 24), beta_g2=(24, 48), gamma_g2=(48, 72), delta_g1=(72, 84), delta_g2=(84, 108))
+        out = {k: (vk[a:b].copy(), bool(inf[i])) for i, (k, (a, b)) in enumerate(off.items())}
+        out["ic"] = ic
+        return out
+
     def free(self):
         if getattr(self, "handle", None) is not None and self.worker.ctx is not None:
             self.worker.lib.b200zk_crs_free(self.handle)
@@ -796,6 +850,8 @@ def create_proof_from_assignment(worker, params: Parameters, a, b, c, input_assi
     for d in (a_aux_density, b_input_density, b_aux_density):
         dens.append(d.as_bytes() if isinstance(d, DensityTracker) else np.ascontiguousarray(d, dtype=np.uint8))
     assert dens[0].shape[0] == aux.shape[0] and dens[1].shape[0] == inputs.shape[0] and dens[2].shape[0] == aux.shape[0]
+    if b.shape[0] != a.shape[0] or c.shape[0] != a.shape[0] or a.shape[0] == 0 or inputs.shape[0] == 0:
+        raise ValueError("a, b and c must hold one evaluation per constraint (equal, non-zero lengths) and there is at least the input ONE")
     rl = np.array([(r >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
     sl = np.array([(s >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
     pa, pb, pc = np.zeros(12, np.uint64), np.zeros(24, np.uint64), np.zeros(12, np.uint64)
@@ -839,6 +895,35 @@ def create_proofs_from_assignments(worker, params: Parameters, assignments, lock
     if st:
         _raise(worker, st)
     return [Proof(pa[i], pb[i], pc[i], inf[i]) for i in range(n)]
+
+
+def create_proof_bytes_from_assignments(worker, params: Parameters, assignments, lockstep=0):
+    """The batch as the outer FFI sees it (rustzcash.rs:1375-1626 -> create_random_proof -> Proof::write): a sequence of assignment
+    tuples in, the list of 192-byte proofs out (b200zk_groth16_prove_batch_bytes: proved in lock-step groups, encoded on the device)."""
+    n = len(assignments)
+    if n == 0:
+        return []
+    keep, rows = [], (L.ProveInput * n)()
+    shape = None
+    for i, (a, b, c, inputs, aux, da, dbi, dba, r, s) in enumerate(assignments):
+        a, b, c, inputs, aux = _u64(a, 4), _u64(b, 4), _u64(c, 4), _u64(inputs, 4), _u64(aux, 4)
+        dens = [d.as_bytes() if isinstance(d, DensityTracker) else np.ascontiguousarray(d, dtype=np.uint8) for d in (da, dbi, dba)]
+        this = (a.shape[0], inputs.shape[0], aux.shape[0])
+        if shape is None:
+            shape = this
+        if this != shape or b.shape[0] != shape[0] or c.shape[0] != shape[0] or dens[0].shape[0] != shape[2] or dens[1].shape[0] != shape[1] or dens[2].shape[0] != shape[2]:
+            raise ValueError("the proofs of a batch must come from the same circuit (equal sizes)")
+        rl = np.array([(r >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+        sl = np.array([(s >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+        arrs = (a, b, c, inputs, aux, dens[0], dens[1], dens[2], rl, sl)
+        keep.append(arrs)
+        for (name, _), arr in zip(L.ProveInput._fields_, arrs):
+            setattr(rows[i], name, arr.ctypes.data)
+    out = np.zeros(192 * n, dtype=np.uint8)
+    st = worker.lib.b200zk_groth16_prove_batch_bytes(worker.ctx, params.handle, C.cast(rows, C.c_void_p), n, shape[0], shape[1], shape[2], lockstep, _ptr(out))
+    if st:
+        _raise(worker, st)
+    return [out[192 * i:192 * (i + 1)].tobytes() for i in range(n)]
 
 
 # ------------------------------------------------------------------------------------------- circuit-facing prover API

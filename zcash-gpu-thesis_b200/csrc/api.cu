@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <dlfcn.h>
 
 #include "internal.h"
@@ -797,6 +798,7 @@ int b200zk_crs_create(b200zk_ctx *ctx, const b200zk_bases *h, const b200zk_bases
     c->b_g1 = const_cast<b200zk_bases *>(b_g1); c->b_g2 = const_cast<b200zk_bases *>(b_g2);
     c->vk = c->table_delta_g1 = c->table_delta_g2 = nullptr;
     c->subverted = vk_infinity && (vk_infinity[3] || vk_infinity[4]);
+    if (vk_infinity) memcpy(c->vk_inf, vk_infinity, 5);
     const size_t t1 = (size_t)32 * 255 * 192, t2 = (size_t)32 * 255 * 384;
     if (cudaMalloc(&c->vk, 3 * 96 + 2 * 192) != cudaSuccess || cudaMalloc(&c->table_delta_g1, t1) != cudaSuccess ||
         cudaMalloc(&c->table_delta_g2, t2) != cudaSuccess) {
@@ -827,6 +829,8 @@ void b200zk_crs_free(b200zk_crs *crs) {
     cudaFree(crs->vk);
     cudaFree(crs->table_delta_g1);
     cudaFree(crs->table_delta_g2);
+    if (crs->owns_bases)
+        for (Bases *b : {crs->h, crs->l, crs->a, crs->b_g1, crs->b_g2}) b200zk_bases_free(static_cast<b200zk_bases *>(b));
     delete crs;
 }
 
@@ -869,6 +873,30 @@ int b200zk_groth16_prove_batch(b200zk_ctx *ctx, const b200zk_crs *crs, const b20
         int rc = groth16_prove_batch(ctx, crs, args.data(), (uint32_t)K, proofs_a + 12 * first, proofs_b + 24 * first, proofs_c + 12 * first,
                                      inf_flags ? inf_flags + 3 * first : nullptr);
         if (rc) return rc;
+    }
+    return B200ZK_OK;
+}
+
+// The batch as the outer FFI sees it (librustzcash_sapling_spend_proof, rustzcash.rs:1375-1626, ends in create_random_proof and
+// Proof::write into a 192-byte buffer, rustzcash.rs:1556-1601): N assignments in, N x 192 proof bytes out.
+int b200zk_groth16_prove_batch_bytes(b200zk_ctx *ctx, const b200zk_crs *crs, const b200zk_prove_input *proofs, size_t n_proofs, size_t n_constraints,
+                                     size_t n_inputs, size_t n_aux, int lockstep, uint8_t *out_proofs /* n_proofs x 192 */) {
+    CHECK_CTX(ctx);
+    if (n_proofs && !out_proofs) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null output");
+    if (n_proofs == 0) return B200ZK_OK;
+    std::vector<uint64_t> a(12 * n_proofs), b(24 * n_proofs), c(12 * n_proofs);
+    std::vector<uint8_t> inf(3 * n_proofs), fa(n_proofs), fb(n_proofs), fc(n_proofs);
+    int rc = b200zk_groth16_prove_batch(ctx, crs, proofs, n_proofs, n_constraints, n_inputs, n_aux, lockstep, a.data(), b.data(), c.data(), inf.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < n_proofs; i++) { fa[i] = inf[3 * i]; fb[i] = inf[3 * i + 1]; fc[i] = inf[3 * i + 2]; }
+    std::vector<uint8_t> ea(48 * n_proofs), eb(96 * n_proofs), ec(48 * n_proofs);
+    if ((rc = b200zk_encode_points(ctx, B200ZK_G1, a.data(), fa.data(), n_proofs, 1, ea.data()))) return rc;
+    if ((rc = b200zk_encode_points(ctx, B200ZK_G2, b.data(), fb.data(), n_proofs, 1, eb.data()))) return rc;
+    if ((rc = b200zk_encode_points(ctx, B200ZK_G1, c.data(), fc.data(), n_proofs, 1, ec.data()))) return rc;
+    for (size_t i = 0; i < n_proofs; i++) {  // Proof::write: a (48) | b (96) | c (48), groth16/mod.rs:43-53
+        memcpy(out_proofs + 192 * i, ea.data() + 48 * i, 48);
+        memcpy(out_proofs + 192 * i + 48, eb.data() + 96 * i, 96);
+        memcpy(out_proofs + 192 * i + 144, ec.data() + 48 * i, 48);
     }
     return B200ZK_OK;
 }

@@ -65,14 +65,14 @@ __device__ g1_jac_t jacobian_mul(const g1_jac_t &p, const uint32_t *k) {
 //   k_proof_c  (after all):  proof.c = affine(sga + rb1 + H + L)
 // One block per proof of the batch (blockIdx.x = k): scal[16 k ..] = r_k, s_k; every result array is indexed by k.
 __global__ void __launch_bounds__(32) k_proof_a(const g1_xyzz_t *table_d1, const uint32_t *scal, const g1_affine_t *vk_g1 /* alpha, beta, delta */,
-                                               const g1_jac_t *res_a, g1_jac_t *sga, g1_affine_t *proof_a, uint8_t *inf_flags) {
+                                               bool alpha_inf, const g1_jac_t *res_a, g1_jac_t *sga, g1_affine_t *proof_a, uint8_t *inf_flags) {
     __shared__ g1_xyzz_t sm[32];
     const uint32_t k = blockIdx.x;
     scal += 16 * k;
     g1_xyzz_t t;
     table_mul_warp<fq_t>(table_d1, scal, sm, t);
     if (threadIdx.x != 0) return;
-    t.add_mixed(vk_g1[0], false);
+    if (!alpha_inf) t.add_mixed(vk_g1[0], false);  // add_assign_mixed skips an identity operand (ec.rs:447-449)
     t.add(g1_xyzz_t::from_jacobian(res_a[k]));
     const g1_jac_t ga = t.to_jacobian();
     g1_affine_t a;
@@ -82,23 +82,23 @@ __global__ void __launch_bounds__(32) k_proof_a(const g1_xyzz_t *table_d1, const
     sga[k] = jacobian_mul(ga, scal + 8);
 }
 
-__global__ void __launch_bounds__(32) k_proof_b1(const uint32_t *scal, const g1_affine_t *vk_g1, const g1_jac_t *res_b1, g1_jac_t *rb1) {
+__global__ void __launch_bounds__(32) k_proof_b1(const uint32_t *scal, const g1_affine_t *vk_g1, bool beta_inf, const g1_jac_t *res_b1, g1_jac_t *rb1) {
     if (threadIdx.x != 0) return;
     const uint32_t k = blockIdx.x;
-    g1_xyzz_t b1 = g1_xyzz_t::from_affine(vk_g1[1]);
+    g1_xyzz_t b1 = beta_inf ? g1_xyzz_t::zero() : g1_xyzz_t::from_affine(vk_g1[1]);
     b1.add(g1_xyzz_t::from_jacobian(res_b1[k]));
     rb1[k] = jacobian_mul(b1.to_jacobian(), scal + 16 * k);
 }
 
 __global__ void __launch_bounds__(32) k_proof_b(const g2_xyzz_t *table_d2, const uint32_t *scal, const g2_affine_t *vk_g2 /* beta, delta */,
-                                               const g2_jac_t *res_b2, g2_affine_t *proof_b, uint8_t *inf_flags) {
+                                               bool beta_inf, const g2_jac_t *res_b2, g2_affine_t *proof_b, uint8_t *inf_flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     g2_xyzz_t *sm = reinterpret_cast<g2_xyzz_t *>(smem_raw);
     const uint32_t k = blockIdx.x;
     g2_xyzz_t t;
     table_mul_warp<fq2_t>(table_d2, scal + 16 * k + 8, sm, t);
     if (threadIdx.x != 0) return;
-    t.add_mixed(vk_g2[0], false);
+    if (!beta_inf) t.add_mixed(vk_g2[0], false);
     t.add(g2_xyzz_t::from_jacobian(res_b2[k]));
     g2_affine_t a;
     bool ok = jacobian_to_affine_serial(t.to_jacobian(), a);
@@ -247,17 +247,20 @@ int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_
             B200ZK_CUDA(ctx, cudaStreamWaitEvent(on->stream, ctx->ev_fork, 0));
         }
         const unsigned long long before = on->launches;
-        if ((rc = msm_run(on, jobs[j].b, 0, w + jobs[j].src, jobs[j].n, jobs[j].d, w + jobs[j].out, stw + (size_t)j * K, 0, jobs[j].batch)))
+        if ((rc = msm_run(on, jobs[j].b, 0, w + jobs[j].src, jobs[j].n, jobs[j].d, w + jobs[j].out, stw + (size_t)j * K, 0, jobs[j].batch))) {
+            for (Ctx *lane : ctx->lanes) cudaStreamSynchronize(lane->stream);  // other lanes still read this call's workspace
+            cudaStreamSynchronize(st);
             return on == ctx ? rc : set_error(ctx, rc, on->last_error);
+        }
         static const char *const msm_names[] = {"multiexp H", "multiexp L", "multiexp A", "multiexp B-G1", "multiexp B-G2"};
         static const char *const piece_names[] = {"", "", "piece a (g_a, s*g_a)", "piece b1 (r*B1)", "piece b (g_b)"};
         trace.mark(msm_names[j], on->stream);
         // the piece of the assembly (prover.rs:326-363) that only needs this multiexp
         if (j == 2)
-            k_proof_a<<<K, 32, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, (const g1_jac_t *)(w + o_ra), sga, (g1_affine_t *)(w + o_pa), dinf);
-        if (j == 3) k_proof_b1<<<K, 32, 0, on->stream>>>(scal, vk1, (const g1_jac_t *)(w + o_rb1), rb1);
+            k_proof_a<<<K, 32, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, crs->vk_inf[0] != 0, (const g1_jac_t *)(w + o_ra), sga, (g1_affine_t *)(w + o_pa), dinf);
+        if (j == 3) k_proof_b1<<<K, 32, 0, on->stream>>>(scal, vk1, crs->vk_inf[1] != 0, (const g1_jac_t *)(w + o_rb1), rb1);
         if (j == 4)
-            k_proof_b<<<K, 32, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, (const g2_jac_t *)(w + o_rb2),
+            k_proof_b<<<K, 32, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, crs->vk_inf[2] != 0, (const g2_jac_t *)(w + o_rb2),
                                                                     (g2_affine_t *)(w + o_pb), dinf);
         if (j >= 2) { on->launches++; trace.mark(piece_names[j], on->stream); }
         if (on != ctx) ctx->launches += on->launches - before;

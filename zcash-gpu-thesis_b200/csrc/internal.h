@@ -129,6 +129,13 @@ struct Crs {
     void *table_delta_g1;  // 32 x 255 XYZZ<fq>
     void *table_delta_g2;  // 32 x 255 XYZZ<fq2>
     bool subverted;      // delta_g1 or delta_g2 is the identity (prover.rs:320-324)
+    uint8_t vk_inf[5] = {0, 0, 0, 0, 0};  // infinity flags of alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2 (add_assign_mixed skips an identity, ec.rs:447-449)
+    // Parameters::read keeps the whole VerifyingKey (groth16/mod.rs:100-126) for Parameters::write and for the verifier:
+    bool owns_bases = false;           // the five query vectors were created by b200zk_parameters_read and are freed with the CRS
+    bool has_full_vk = false;
+    uint64_t vk_host[108] = {};        // alpha_g1 | beta_g1 | beta_g2 | gamma_g2 | delta_g1 | delta_g2 (affine x||y, Montgomery)
+    uint8_t vk_host_inf[6] = {};
+    std::vector<uint64_t> ic;          // 12 words per element
 };
 struct ProveArgs {
     const uint64_t *a, *b, *c; size_t n_constraints;
