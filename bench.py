@@ -379,6 +379,24 @@ class BenchEnv:
         self.w, self.lib, self.zk, self.L, self.torch, self.dist, self.barrier, self.timed = w, lib, zk, L, torch, dist, barrier, timed
 
 
+def single_gpu_env(w, zk, no_cpu=True):
+    """a BenchEnv for the tools/ scripts: one rank, no torch.distributed"""
+    import types
+
+    from zcash_gpu_thesis_b200 import _lib as L
+
+    args = types.SimpleNamespace(no_cpu=no_cpu, steps=5, warmup=3, log_n=24)
+
+    def timed(fn, steps):
+        w.sync()
+        w.timer_start()
+        for _ in range(steps):
+            fn()
+        return w.timer_stop()
+
+    return BenchEnv(args, 0, 1, 0, w, w.lib, zk, L, None, None, w.sync, timed)
+
+
 class MsmWorkload:
     """One rank's shard of a G1 (or G2) multiexp: n bases [k_i] * generator generated on the device and kept resident (with the
     precomputed table), n uniform scalars in pinned host memory and in HBM."""
@@ -422,6 +440,7 @@ class MsmWorkload:
         lg = self.n.bit_length() - 1
         if self.t_pre is not None:
             c = min(22, max(8, lg if lg < 19 else lg - 1))
+            c += 1 if 255 % c == 0 else 0
         else:
             c = 16 if lg >= 23 else 15 if lg >= 22 else 14
         return c, (256 + c - 1) // c

@@ -10,4 +10,4 @@ import bench
 import zcash_gpu_thesis_b200 as zk
 
 w = zk.Worker(0)
-print(bench.bench_spend_proofs(w, zk, np.random.default_rng(5), 1)["batched"])
+print(bench.bench_spend_proofs(bench.single_gpu_env(w, zk), np.random.default_rng(5))["batched"])

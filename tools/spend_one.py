@@ -11,5 +11,5 @@ streams = int(sys.argv[1]) if len(sys.argv) > 1 else None
 if streams:
     import types
     src = open(bench.__file__).read()
-out = bench.bench_spend_proofs(w, zk, rng, 1)
+out = bench.bench_spend_proofs(bench.single_gpu_env(w, zk), rng)
 print(json.dumps(out))

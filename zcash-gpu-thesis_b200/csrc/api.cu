@@ -277,6 +277,9 @@ int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bit
         if (const char *e = getenv("B200ZK_PRE_DELTA")) c = lg - (uint32_t)atoi(e);
         if (c < 8) c = 8;
         if (c > 22) c = 22;
+        // 255 = 15 x 17: with c = 15 or 17 the scalar fills its windows exactly and the signed-digit carry of the last one lands in
+        // an extra window whose only bucket (digit 1) then receives half of all the points; one bit more avoids that
+        if (255 % c == 0) c++;
     }
     return msm_precompute(ctx, bases, c);
 }

@@ -341,90 +341,62 @@ __global__ void __launch_bounds__(COMBINE_BIG_THREADS) k_msm_combine_big(const u
 }
 
 // ------------------------------------------------------------------------------------------------ bucket reduction
-// For a range [lo, hi) of buckets: R = sum S_i, A = sum (i - lo) S_i.  A parent over K children of length `len`:
-// R = sum R_j, A = sum A_j + len * sum j R_j (running sum, then log2(len) doublings).  Window sum = A + R.
-static constexpr uint32_t RED_K = 8, RED_LOG_K = 3;  // short serial chains per thread: the tree is latency-bound, not work-bound
+// The reference folds a window's buckets with a running sum (multiexp.rs:202-206): 2 (2^c - 1) dependent additions.  On the GPU
+// a dependent point addition costs ~10 us (G1) / ~25 us (G2) of latency in one thread, so the reduction is arranged for DEPTH:
+//
+//   sum_i (i + 1) E_i  =  R + sum_j 2^j T_j ,   R = sum_i E_i ,   T_j = sum over {i : bit j of i} E_i          (E_i = bucket i + 1)
+//
+// computed as a pairwise ladder: C^0 = E, C^(s+1)_k = C^s_2k + C^s_(2k+1) (so C^s_k is the sum of the buckets whose index,
+// shifted right by s, is k), and T_s = the sum of the ODD entries of C^s, itself a pairwise tree that starts in the same step
+// and stays one halving behind.  Every step is one launch in which every thread does ONE addition; after log2(B) - 1 steps all
+// T_j and R are known.  2 B additions in total (as many as the running sum), log2(B) deep instead of 2 B.
+// (Round 1 used an 8-ary (R, A) tree above 4096 entries and computed all masked sums at once below: ~3 x deeper, 17 x the
+// additions on the last 4096 entries.)
 template <class F>
-__global__ void __launch_bounds__(64) k_msm_reduce_level(const XYZZ<F> *__restrict__ inR, const XYZZ<F> *__restrict__ inA, uint32_t n_in,
-                                                        XYZZ<F> *__restrict__ outR, XYZZ<F> *__restrict__ outA, uint32_t n_out, uint32_t W,
-                                                        uint32_t log_len) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_out * W) return;
-    uint32_t w = t / n_out, p = t % n_out;
-    uint32_t first = p * RED_K, last = first + RED_K < n_in ? first + RED_K : n_in;
-    const XYZZ<F> *R = inR + (size_t)w * n_in;
-    XYZZ<F> run = XYZZ<F>::zero(), accw = XYZZ<F>::zero();
-    for (uint32_t j = last; j-- > first + 1;) {
-        run.add(R[j]);
-        accw.add(run);
+__global__ void __launch_bounds__(64) k_msm_ladder_step(const XYZZ<F> *__restrict__ Cin, const XYZZ<F> *__restrict__ Din, uint32_t m, uint32_t s, uint32_t sets,
+                                                       XYZZ<F> *__restrict__ Cout, XYZZ<F> *__restrict__ Dout) {
+    // per bucket set: m / 2 pair sums of C, and (s + 1) arrays of nD = m / 4 pair sums of the odd-entry trees
+    const uint32_t nC = m >> 1, nD = m >> 2, per_set = nC + (s + 1) * nD;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per_set * sets) return;
+    const uint32_t w = t / per_set, u = t % per_set;
+    const XYZZ<F> *C = Cin + (size_t)w * m;
+    XYZZ<F> acc;
+    if (u < nC) {
+        acc = C[2 * u];
+        acc.add(C[2 * u + 1]);
+        Cout[(size_t)w * nC + u] = acc;
+        return;
     }
-    run.add(R[first]);
-    for (uint32_t d = 0; d < log_len; d++) accw.dbl();
-    if (inA) {
-        const XYZZ<F> *A = inA + (size_t)w * n_in;
-        for (uint32_t j = first; j < last; j++) accw.add(A[j]);
+    const uint32_t j = (u - nC) / nD, k = (u - nC) % nD;
+    if (j == s) {  // the tree of T_s starts from the odd entries of C^s
+        acc = C[4 * k + 1];
+        acc.add(C[4 * k + 3]);
+    } else {       // the tree of T_j, j < s: one more halving (its arrays hold 2 nD entries in Din)
+        const XYZZ<F> *D = Din + ((size_t)w * s + j) * (2 * nD);
+        acc = D[2 * k];
+        acc.add(D[2 * k + 1]);
     }
-    outR[t] = run;
-    outA[t] = accw;
+    Dout[((size_t)w * (s + 1) + j) * nD + k] = acc;
 }
-
-// ---- bit-sliced tail of the bucket reduction --------------------------------------------------------------------------
-// Once a window is down to n <= SLICE_MAX entries (R_i, A_i) the 8-ary tree would still cost ~30 serial point operations
-// per level; a single thread needs ~10 us per point addition, so small multiexps (a Sapling proof's are ~10^5 points) were
-// spending most of their time here.  sum_i i R_i = sum_j 2^j T_j with T_j = sum over {i : bit j of i} R_i: all T_j, sum R_i and
-// sum A_i are plain sums, computed together by log2(n) levels of one addition each (k_msm_slice_sum; the levels are pure
-// latency: fan-in 2 measured faster than 3, 4 and 8 despite the extra launches), then the warp-parallel k_msm_slice_final.
-static constexpr uint32_t SLICE_MAX = 4096;
-#ifndef B200ZK_SLICE_FAN
-#define B200ZK_SLICE_FAN 2
-#endif
-static constexpr uint32_t SLICE_FAN = B200ZK_SLICE_FAN;  // entries folded per thread and level of the sliced sums
-// slice s < nb: masked sum of R (bit s of the index); s == nb: sum of R; s == nb + 1: sum of A.
-// first level: in = R / A arrays of n_in entries per window; later levels: in = previous Y ((nb + 2) rows of n_in per window)
+// The last step and the weights: C (2 entries) and the finished trees D (nb - 1 single entries) of one bucket set ->
+// value = (C_0 + C_1) + 2^(nb-1) C_1 + sum_(j < nb-1) 2^j T_j, written as the (R, A) pair (value, 0) that k_msm_window_combine takes.
+// One warp per bucket set: lane j raises its term to its power of two by j doublings, a shared-memory tree adds the terms.
 template <class F>
-__global__ void __launch_bounds__(64) k_msm_slice_sum(const XYZZ<F> *__restrict__ R, const XYZZ<F> *__restrict__ A, const XYZZ<F> *__restrict__ Yin,
-                                                     uint32_t n_in, uint32_t nb, uint32_t n_out, uint32_t W, XYZZ<F> *__restrict__ Yout) {
-    const uint32_t S = nb + 2;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= W * S * n_out) return;
-    uint32_t c = t % n_out, s = (t / n_out) % S, w = t / (n_out * S);
-    uint32_t first = c * SLICE_FAN, last = min(first + SLICE_FAN, n_in);
-    XYZZ<F> acc = XYZZ<F>::zero();
-    if (Yin) {
-        const XYZZ<F> *src = Yin + ((size_t)w * S + s) * n_in;
-        for (uint32_t i = first; i < last; i++) acc.add(src[i]);
-    } else if (s < nb) {
-        const XYZZ<F> *src = R + (size_t)w * n_in;
-        for (uint32_t i = first; i < last; i++) if ((i >> s) & 1) acc.add(src[i]);
-    } else if (s == nb) {
-        const XYZZ<F> *src = R + (size_t)w * n_in;
-        for (uint32_t i = first; i < last; i++) acc.add(src[i]);
-    } else if (A) {
-        const XYZZ<F> *src = A + (size_t)w * n_in;
-        for (uint32_t i = first; i < last; i++) acc.add(src[i]);
-    }
-    Yout[((size_t)w * S + s) * n_out + c] = acc;
-}
-// window value = sum A_i + sum R_i + 2^log_len * sum_j 2^j T_j ; written as the (R, A) pair (value, 0) that k_msm_window_combine takes.
-// One warp per bucket set: lane j raises T_j to its power of two by j + log_len doublings, lanes nb and nb + 1 carry the two
-// plain sums, and a shared-memory tree adds the 32 terms -- a third fewer dependent point operations than the one-thread
-// Horner rule it replaces (this kernel is pure latency: ~1 ms of a 61 000-point G2 multiexp).
-template <class F>
-__global__ void __launch_bounds__(32) k_msm_slice_final(const XYZZ<F> *__restrict__ Y, uint32_t nb, uint32_t log_len, uint32_t W, XYZZ<F> *__restrict__ outR,
-                                                       XYZZ<F> *__restrict__ outA) {
+__global__ void __launch_bounds__(32) k_msm_ladder_final(const XYZZ<F> *__restrict__ C, const XYZZ<F> *__restrict__ D, uint32_t nb, uint32_t sets, XYZZ<F> *__restrict__ outR,
+                                                        XYZZ<F> *__restrict__ outA) {
     __shared__ XYZZ<F> sm[32];
     const uint32_t w = blockIdx.x, j = threadIdx.x;
-    if (w >= W) return;
-    const XYZZ<F> *y = Y + (size_t)w * (nb + 2);
+    if (w >= sets) return;
     XYZZ<F> acc = XYZZ<F>::zero();
-    if (nb + 2 <= 32) {
-        if (j < nb + 2) acc = y[j];
-        if (j < nb) for (uint32_t d = 0; d < j + log_len; d++) acc.dbl();
-    } else if (j == 0) {  // more than 30 slices cannot happen (SLICE_MAX <= 2^30); kept for safety: the serial rule
-        for (uint32_t k = nb; k-- > 0;) { acc.dbl(); acc.add(y[k]); }
-        for (uint32_t d = 0; d < log_len; d++) acc.dbl();
-        acc.add(y[nb]);
-        acc.add(y[nb + 1]);
+    if (nb == 0) {  // a single bucket (c = 1 never happens; kept for completeness)
+        if (j == 0) acc = C[w];
+    } else {
+        const XYZZ<F> *c2 = C + (size_t)w * 2;
+        if (j + 1 < nb) acc = D[(size_t)w * (nb - 1) + j];        // T_j
+        else if (j + 1 == nb) acc = c2[1];                        // T_(nb-1) = the odd entry of the last C
+        else if (j == nb) { acc = c2[0]; acc.add(c2[1]); }        // R
+        if (j < nb) for (uint32_t d = 0; d < j; d++) acc.dbl();
     }
     sm[j] = acc;
     __syncthreads();
@@ -483,7 +455,8 @@ static uint32_t msm_default_window(size_t n) {
     if (n < (1u << 18)) return 12;
     if (n < (1u << 20)) return 13;
     if (n < (1u << 22)) return 14;
-    if (n < (1u << 23)) return 15;
+    // never 15 or 17: 255 = 15 x 17, so with those widths the signed-digit carry of the top window gets a window of its own, whose
+    // single bucket receives half of all the points
     return 16;
 }
 
@@ -527,9 +500,12 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     {
         // A small multiexp cannot fill the machine with one thread per bucket: its time is (longest chain) x (latency of one
         // dependent point addition).  Cut the chains so that there are about `waves` tasks per resident thread slot.
-        double waves = 0.0;  // off: since the cap follows the actual histogram (k_msm_pick_cap) cutting every chain no longer pays (Spend proofs 250 vs 230 /s)
-        if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
+        // Automatic for multiexps with fewer than 64 additions per resident thread (a Spend proof's multiexps, a strong-scaling
+        // shard): measured on B200, two waves of tasks: G1 2^16 1.53 -> 1.26 ms, G2 61 300 points 5.9 -> 4.8 ms.  Large
+        // multiexps are throughput-bound and keep whole buckets (splitting only adds partial sums to fold).
         const size_t slots = (size_t)ctx->sm_count * AccShape<F>::MINBLOCKS * AccShape<F>::THREADS;
+        double waves = refs_max < 64 * slots ? 2.0 : 0.0;
+        if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
         if (waves > 0) {
             const size_t fill = (size_t)((double)refs_max / (waves * (double)slots));
             cap = (uint32_t)std::min<size_t>(cap, std::max<size_t>(8, fill));
@@ -540,14 +516,13 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_tcnt = take((nbk + 1) * sizeof(uint32_t)), o_toff = take((nbk + 1) * sizeof(uint32_t));
     size_t o_split = take((nbk + 1) * sizeof(uint32_t)), o_partials = take(max_tasks * sizeof(XYZZ<F>));
     size_t o_shist = take((cap + 2) * sizeof(uint32_t)), o_scur = take((cap + 2) * sizeof(uint32_t)), o_order = take((nbk + 1) * sizeof(uint32_t));
-    size_t lvl_entries = (size_t)bw * ((sh.B + RED_K - 1) / RED_K) + bw;
-    size_t o_r0 = take(lvl_entries * sizeof(XYZZ<F>)), o_a0 = take(lvl_entries * sizeof(XYZZ<F>));
-    size_t o_r1 = take(lvl_entries * sizeof(XYZZ<F>)), o_a1 = take(lvl_entries * sizeof(XYZZ<F>));
-    uint32_t slice_max = SLICE_MAX;
-    if (const char *e = getenv("B200ZK_SLICE_MAX")) slice_max = (uint32_t)std::max(8, atoi(e));
-    const size_t slice_n = std::min<size_t>(sh.B, slice_max);
-    const size_t y_entries = (size_t)bw * 18 * ((slice_n + SLICE_FAN - 1) / SLICE_FAN) + 64;  // (nb + 2 <= 17) rows of n / SLICE_FAN sums per window
-    size_t o_y0 = take(y_entries * sizeof(XYZZ<F>)), o_y1 = take((y_entries / SLICE_FAN + 64 * (size_t)bw * 18) * sizeof(XYZZ<F>));
+    // reduction ladder: C ping-pong (B / 2 and B / 4 entries per set), the odd-entry trees ping-pong (<= B / 4 entries per set each)
+    const size_t half_b = std::max<size_t>(sh.B / 2, 1), quarter_b = std::max<size_t>(sh.B / 4, 1);
+    uint32_t log_b = 0;
+    while ((1u << log_b) < sh.B) log_b++;
+    size_t o_c0 = take((size_t)bw * half_b * sizeof(XYZZ<F>)), o_c1 = take((size_t)bw * quarter_b * sizeof(XYZZ<F>));
+    size_t o_d0 = take((size_t)bw * quarter_b * sizeof(XYZZ<F>)), o_d1 = take((size_t)bw * quarter_b * sizeof(XYZZ<F>));
+    size_t o_fr = take((size_t)bw * sizeof(XYZZ<F>)), o_fa = take((size_t)bw * sizeof(XYZZ<F>));
     // batched-affine accumulation (msm_batched_affine.cuh): correct (the whole MSM suite passes with B200ZK_BA=1) but, as
     // measured on B200 at 2^24 (accumulation 90.5 ms vs 76.7 ms for the XYZZ kernel), slower: its two passes over the
     // points are bound by dependent gathers, not by the multiplier pipe.  Opt-in only.
@@ -565,7 +540,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     uint32_t *task_cnt = (uint32_t *)(ws + o_tcnt), *task_off = (uint32_t *)(ws + o_toff), *split_list = (uint32_t *)(ws + o_split);
     XYZZ<F> *partials = (XYZZ<F> *)(ws + o_partials);
     uint32_t *size_hist = (uint32_t *)(ws + o_shist), *size_cur = (uint32_t *)(ws + o_scur), *order = (uint32_t *)(ws + o_order);
-    XYZZ<F> *lr[2] = {(XYZZ<F> *)(ws + o_r0), (XYZZ<F> *)(ws + o_r1)}, *la[2] = {(XYZZ<F> *)(ws + o_a0), (XYZZ<F> *)(ws + o_a1)};
+    XYZZ<F> *lc[2] = {(XYZZ<F> *)(ws + o_c0), (XYZZ<F> *)(ws + o_c1)}, *ld[2] = {(XYZZ<F> *)(ws + o_d0), (XYZZ<F> *)(ws + o_d1)};
 
     B200ZK_CUDA(ctx, cudaMemsetAsync(status + ST_PER_K, 0xff, 3 * (size_t)K * sizeof(uint32_t), st));
     if (n_exp == 0) {
@@ -626,41 +601,20 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         k_msm_combine_big<F><<<256, COMBINE_BIG_THREADS, big_smem, st>>>(split_list, n_split, (uint32_t)nbk, task_cnt, task_off, partials, buckets);
     }
     if (ctx->prof_on) { cudaEventRecord(pe1, st); ctx->prof_events.emplace_back(pe0, pe1); }
-    // reduction: 8-ary (R, A) tree while a window has more than SLICE_MAX entries, then the bit-sliced sums
-    const XYZZ<F> *inR = buckets, *inA = nullptr;
-    uint32_t n_in = sh.B, log_len = 0;
-    int pp = 0;
-    while (n_in > slice_max) {
-        uint32_t n_out = (n_in + RED_K - 1) / RED_K;
-        uint32_t threads = n_out * bw;
-        k_msm_reduce_level<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, n_in, lr[pp], la[pp], n_out, bw, log_len);
+    // reduction ladder (see k_msm_ladder_step): log2(B) - 1 one-addition steps, then the weights
+    const XYZZ<F> *cin = buckets, *din = nullptr;
+    uint32_t m = sh.B;
+    for (uint32_t step = 0; m > 2; step++, m >>= 1) {
+        const size_t threads = (size_t)bw * ((m >> 1) + (size_t)(step + 1) * (m >> 2));
+        XYZZ<F> *cout = lc[step & 1], *dout = ld[step & 1];
+        k_msm_ladder_step<F><<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(cin, din, m, step, bw, cout, dout);
         ctx->launches++;
-        inR = lr[pp]; inA = la[pp];
-        pp ^= 1;
-        n_in = n_out;
-        log_len += RED_LOG_K;
+        cin = cout;
+        din = dout;
     }
-    {
-        uint32_t nb = 0;
-        while ((1u << nb) < n_in) nb++;
-        const uint32_t S = nb + 2;
-        XYZZ<F> *ys[2] = {(XYZZ<F> *)(ws + o_y0), (XYZZ<F> *)(ws + o_y1)};
-        const XYZZ<F> *yin = nullptr;
-        int yp = 0;
-        uint32_t cur = n_in;
-        do {
-            uint32_t n_out = (cur + SLICE_FAN - 1) / SLICE_FAN;
-            uint32_t threads = bw * S * n_out;
-            k_msm_slice_sum<F><<<(threads + 63) / 64, 64, 0, st>>>(inR, inA, yin, cur, nb, n_out, bw, ys[yp]);
-            ctx->launches++;
-            yin = ys[yp];
-            yp ^= 1;
-            cur = n_out;
-        } while (cur > 1);
-        k_msm_slice_final<F><<<bw, 32, 0, st>>>(yin, nb, log_len, bw, lr[pp], la[pp]);
-        ctx->launches++;
-        inR = lr[pp]; inA = la[pp];
-    }
+    XYZZ<F> *inR = (XYZZ<F> *)(ws + o_fr), *inA = (XYZZ<F> *)(ws + o_fa);
+    k_msm_ladder_final<F><<<bw, 32, 0, st>>>(cin, din, sh.B >= 2 ? log_b : 0u, bw, inR, inA);
+    ctx->launches++;
     k_msm_window_combine<F><<<K, 1, 0, st>>>(inR, inA, sh, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
