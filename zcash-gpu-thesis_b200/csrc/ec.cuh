@@ -126,6 +126,150 @@ struct XYZZ {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ two lanes per point
+// A dependent point addition in ONE thread is a ~10 us (G1) / ~25 us (G2) chain of field products, and everything that is not
+// the big bucket accumulation (the chains of a small multiexp, the bucket reduction, the window combination, the scalar
+// multiplications of the proof assembly) is bound by that latency, not by throughput.  PairXYZZ splits one XYZZ point over two
+// adjacent lanes -- lane 0 holds (X, ZZ), lane 1 holds (Y, ZZZ) -- so that the formulas' independent products run side by side
+// and the halves meet through warp shuffles:
+//     madd-2008-s   6M + 2S + fused Y3   ->  5 product slots   (U2|S2, PP|RR, PPP|Q, ZZ3|ZZZ3, Y3)
+//     add-2008-s   10M + 2S + fused Y3   ->  7 product slots
+//     dbl-2008-s-1  4M + 3S + fused Y3   ->  4 product slots
+// Both lanes execute every instruction (SIMT); values that only one lane needs are garbage on the other and never used.
+// All 32 lanes of the warp must call these functions together (full-mask shuffles): idle pairs pass the identity / inactive.
+// The exceptional cases of ec.rs:446-526 (equal or opposite points) are rare: when any pair of the warp hits one, both of its
+// lanes gather the whole point and run the single-thread formula.
+__device__ __forceinline__ fq_t lane_select(bool c, const fq_t &x, const fq_t &y) {
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < fq_t::N; i++) r.v[i] = c ? x.v[i] : y.v[i];
+    return r;
+}
+__device__ __forceinline__ fq2_t lane_select(bool c, const fq2_t &x, const fq2_t &y) { return {lane_select(c, x.c0, y.c0), lane_select(c, x.c1, y.c1)}; }
+__device__ __forceinline__ fq_t lane_swap(const fq_t &x) {  // the partner lane's value
+    fq_t r;
+#pragma unroll
+    for (int i = 0; i < fq_t::N; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, x.v[i], 1);
+    return r;
+}
+__device__ __forceinline__ fq2_t lane_swap(const fq2_t &x) { return {lane_swap(x.c0), lane_swap(x.c1)}; }
+
+template <class F>
+struct PairXYZZ {
+    F a, b;  // role 0: (X, ZZ); role 1: (Y, ZZZ)
+    __device__ __forceinline__ static bool role() { return threadIdx.x & 1u; }
+    __device__ __forceinline__ static PairXYZZ zero() { return {F::zero(), F::zero()}; }
+    // identity <=> ZZ == 0 (known to lane 0, told to lane 1)
+    __device__ __forceinline__ bool is_zero() const { return __shfl_sync(0xffffffffu, (int)b.is_zero(), (threadIdx.x & 31u) & ~1u) != 0; }
+    __device__ __forceinline__ static PairXYZZ load(const XYZZ<F> *p) { return role() ? PairXYZZ{p->y, p->zzz} : PairXYZZ{p->x, p->zz}; }
+    __device__ __forceinline__ void store(XYZZ<F> *p) const {
+        if (role()) { p->y = a; p->zzz = b; } else { p->x = a; p->zz = b; }
+    }
+    // both lanes get the whole point (slow paths only)
+    __device__ __forceinline__ XYZZ<F> gather() const {
+        const F pa = lane_swap(a), pb = lane_swap(b);
+        return role() ? XYZZ<F>{pa, a, pb, b} : XYZZ<F>{a, pa, b, pb};
+    }
+    __device__ __forceinline__ static PairXYZZ split(const XYZZ<F> &p) { return role() ? PairXYZZ{p.y, p.zzz} : PairXYZZ{p.x, p.zz}; }
+    __device__ __forceinline__ static PairXYZZ from_affine_half(const F &c2) { return {c2, F::one()}; }
+
+    // this += (x2, y2) affine; c2 = this lane's coordinate of the point (x2 on lane 0; y2, already negated for a negative
+    // digit, on lane 1); active == false leaves the accumulator alone (an idle pair)
+    __device__ __forceinline__ void add_mixed(const F &c2, bool active) {
+        const bool r1 = role();
+        const unsigned lane = threadIdx.x & 31u;
+        const bool self_zero = is_zero();
+        const F t = c2 * b;                              // U2 = x2 ZZ1          | S2 = y2 ZZZ1
+        const F d = t - a;                               // P = U2 - X1          | R = S2 - Y1
+        const bool p_zero = __shfl_sync(0xffffffffu, (int)d.is_zero(), lane & ~1u) != 0;
+        const bool special = active && !self_zero && p_zero;  // same x: doubling or P + (-P) (ec.rs:466-470)
+        const F e = d.sqr();                             // PP                   | RR
+        const F pe = lane_swap(e), pa = lane_swap(a);
+        const F f = lane_select(r1, pa, d) * lane_select(r1, pe, e);  // PPP = P PP   | Q = X1 PP
+        const F pf = lane_swap(f);
+        const F g = b * lane_select(r1, pf, e);          // ZZ3 = ZZ1 PP         | ZZZ3 = ZZZ1 PPP
+        const F x3 = e - pf - f.dbl();                   //                      | X3 = RR - PPP - 2Q
+        const F px3 = lane_swap(x3);
+        const F y3 = mul_sub(d, f - x3, a, pf);          //                      | Y3 = R (Q - X3) - Y1 PPP
+        F na = lane_select(r1, y3, px3), nb = g;
+        if (__any_sync(0xffffffffu, special)) {
+            XYZZ<F> whole = gather();
+            const F pc2 = lane_swap(c2);
+            if (special) {
+                const Affine<F> p = r1 ? Affine<F>{pc2, c2} : Affine<F>{c2, pc2};
+                whole.add_mixed(p, false);
+                const PairXYZZ h = split(whole);
+                na = h.a;
+                nb = h.b;
+            }
+        }
+        const bool take_pt = active && self_zero;        // identity + P = P
+        a = lane_select(take_pt, c2, lane_select(active, na, a));
+        b = lane_select(take_pt, F::one(), lane_select(active, nb, b));
+    }
+
+    // this += o (add-2008-s), all exceptional cases handled
+    __device__ __forceinline__ void add(const PairXYZZ &o) {
+        const bool r1 = role();
+        const unsigned lane = threadIdx.x & 31u;
+        const bool self_zero = is_zero(), other_zero = o.is_zero();
+        const F t1 = a * o.b;                            // U1 = X1 ZZ2          | S1 = Y1 ZZZ2
+        const F t2 = o.a * b;                            // U2 = X2 ZZ1          | S2 = Y2 ZZZ1
+        const F d = t2 - t1;                             // P                    | R
+        const bool p_zero = __shfl_sync(0xffffffffu, (int)d.is_zero(), lane & ~1u) != 0;
+        const bool special = !self_zero && !other_zero && p_zero;
+        const F e = d.sqr();                             // PP                   | RR
+        const F zz = b * o.b;                            // ZZ1 ZZ2              | ZZZ1 ZZZ2
+        const F pe = lane_swap(e), pt1 = lane_swap(t1);
+        const F f = lane_select(r1, pt1, d) * lane_select(r1, pe, e);  // PPP = P PP  | Q = U1 PP
+        const F pf = lane_swap(f);
+        const F g = zz * lane_select(r1, pf, e);         // ZZ3                  | ZZZ3
+        const F x3 = e - pf - f.dbl();                   //                      | X3
+        const F px3 = lane_swap(x3);
+        const F y3 = mul_sub(d, f - x3, t1, pf);         //                      | Y3 = R (Q - X3) - S1 PPP
+        F na = lane_select(r1, y3, px3), nb = g;
+        if (__any_sync(0xffffffffu, special)) {
+            XYZZ<F> whole = gather();
+            const XYZZ<F> other = o.gather();
+            if (special) {
+                whole.add(other);
+                const PairXYZZ h = split(whole);
+                na = h.a;
+                nb = h.b;
+            }
+        }
+        // other = identity: keep this; this = identity: take other
+        a = lane_select(other_zero, a, lane_select(self_zero, o.a, na));
+        b = lane_select(other_zero, b, lane_select(self_zero, o.b, nb));
+    }
+
+    // this = 2 this (dbl-2008-s-1); the identity (all zero) stays the identity by the formulas themselves
+    __device__ __forceinline__ void dbl() {
+        const bool r1 = role();
+        const F u = a.dbl();                             //                      | U = 2 Y1
+        const F q = lane_select(r1, u, a).sqr();         // XX = X1^2            | V = U^2
+        const F pq = lane_swap(q);                       // V                    | XX
+        const F w = lane_select(r1, u, a) * lane_select(r1, q, pq);   // S = X1 V    | W = U V
+        const F mm = q.dbl() + q;                        // M = 3 XX             |
+        const F pmm = lane_swap(mm);                     //                      | M
+        const F r3 = lane_select(r1, w, mm) * lane_select(r1, b, mm);  // M^2        | ZZZ3 = W ZZZ1
+        const F x3 = r3 - w.dbl();                       // X3 = M^2 - 2 S       |
+        const F px3 = lane_swap(x3), pw = lane_swap(w);  //                      | X3, S
+        // lane 0: ZZ3 = V ZZ1 - 0 ; lane 1: Y3 = M (S - X3) - W Y1   (one fused two-product body for both)
+        const F z = F::zero();
+        const F y3 = mul_sub(lane_select(r1, pmm, pq), lane_select(r1, pw - px3, b), lane_select(r1, w, z), lane_select(r1, a, z));
+        a = lane_select(r1, y3, x3);
+        b = lane_select(r1, r3, y3);
+    }
+
+    // Jacobian (X ZZ, Y ZZZ, ZZ) for the C ABI: lane 0 returns X ZZ, lane 1 returns Y ZZZ; *zz_out = ZZ on both lanes
+    __device__ __forceinline__ F to_jacobian_half(F *zz_out) const {
+        const F pb = lane_swap(b);
+        *zz_out = role() ? pb : b;
+        return a * b;
+    }
+};
+
 // ec.rs:586-619 into_affine (one inversion).  Returns false for the identity (x = 0, y = 1 like ec.rs:158-164).
 template <class F>
 __device__ inline bool jacobian_to_affine(const Jacobian<F> &p, Affine<F> &out) {

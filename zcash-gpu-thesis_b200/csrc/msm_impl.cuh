@@ -352,65 +352,77 @@ __global__ void __launch_bounds__(COMBINE_BIG_THREADS) k_msm_combine_big(const u
 // T_j and R are known.  2 B additions in total (as many as the running sum), log2(B) deep instead of 2 B.
 // (Round 1 used an 8-ary (R, A) tree above 4096 entries and computed all masked sums at once below: ~3 x deeper, 17 x the
 // additions on the last 4096 entries.)
+// Every addition of the ladder is done by a PAIR of lanes (ec.cuh PairXYZZ): the steps are pure latency.
 template <class F>
 __global__ void __launch_bounds__(64) k_msm_ladder_step(const XYZZ<F> *__restrict__ Cin, const XYZZ<F> *__restrict__ Din, uint32_t m, uint32_t s, uint32_t sets,
                                                        XYZZ<F> *__restrict__ Cout, XYZZ<F> *__restrict__ Dout) {
     // per bucket set: m / 2 pair sums of C, and (s + 1) arrays of nD = m / 4 pair sums of the odd-entry trees
     const uint32_t nC = m >> 1, nD = m >> 2, per_set = nC + (s + 1) * nD;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= per_set * sets) return;
-    const uint32_t w = t / per_set, u = t % per_set;
-    const XYZZ<F> *C = Cin + (size_t)w * m;
-    XYZZ<F> acc;
-    if (u < nC) {
-        acc = C[2 * u];
-        acc.add(C[2 * u + 1]);
-        Cout[(size_t)w * nC + u] = acc;
-        return;
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;  // two lanes per addition
+    const bool live = t < per_set * sets;
+    const XYZZ<F> *p0 = nullptr, *p1 = nullptr;
+    XYZZ<F> *dst = nullptr;
+    if (live) {
+        const uint32_t w = t / per_set, u = t % per_set;
+        const XYZZ<F> *C = Cin + (size_t)w * m;
+        if (u < nC) {
+            p0 = C + 2 * u; p1 = C + 2 * u + 1;
+            dst = Cout + (size_t)w * nC + u;
+        } else {
+            const uint32_t j = (u - nC) / nD, k = (u - nC) % nD;
+            if (j == s) {  // the tree of T_s starts from the odd entries of C^s
+                p0 = C + 4 * k + 1; p1 = C + 4 * k + 3;
+            } else {       // the tree of T_j, j < s: one more halving (its arrays hold 2 nD entries in Din)
+                const XYZZ<F> *D = Din + ((size_t)w * s + j) * (2 * nD);
+                p0 = D + 2 * k; p1 = D + 2 * k + 1;
+            }
+            dst = Dout + ((size_t)w * (s + 1) + j) * nD + k;
+        }
     }
-    const uint32_t j = (u - nC) / nD, k = (u - nC) % nD;
-    if (j == s) {  // the tree of T_s starts from the odd entries of C^s
-        acc = C[4 * k + 1];
-        acc.add(C[4 * k + 3]);
-    } else {       // the tree of T_j, j < s: one more halving (its arrays hold 2 nD entries in Din)
-        const XYZZ<F> *D = Din + ((size_t)w * s + j) * (2 * nD);
-        acc = D[2 * k];
-        acc.add(D[2 * k + 1]);
-    }
-    Dout[((size_t)w * (s + 1) + j) * nD + k] = acc;
+    PairXYZZ<F> x = live ? PairXYZZ<F>::load(p0) : PairXYZZ<F>::zero();
+    const PairXYZZ<F> y = live ? PairXYZZ<F>::load(p1) : PairXYZZ<F>::zero();
+    x.add(y);
+    if (live) x.store(dst);
 }
 // The last step and the weights: C (2 entries) and the finished trees D (nb - 1 single entries) of one bucket set ->
 // value = (C_0 + C_1) + 2^(nb-1) C_1 + sum_(j < nb-1) 2^j T_j, written as the (R, A) pair (value, 0) that k_msm_window_combine takes.
-// One warp per bucket set: lane j raises its term to its power of two by j doublings, a shared-memory tree adds the terms.
+// 64 threads = 32 lane pairs per bucket set: pair j raises its term to its power of two by j doublings, a shared-memory tree
+// adds the terms.
 template <class F>
-__global__ void __launch_bounds__(32) k_msm_ladder_final(const XYZZ<F> *__restrict__ C, const XYZZ<F> *__restrict__ D, uint32_t nb, uint32_t sets, XYZZ<F> *__restrict__ outR,
+__global__ void __launch_bounds__(64) k_msm_ladder_final(const XYZZ<F> *__restrict__ C, const XYZZ<F> *__restrict__ D, uint32_t nb, uint32_t sets, XYZZ<F> *__restrict__ outR,
                                                         XYZZ<F> *__restrict__ outA) {
     __shared__ XYZZ<F> sm[32];
-    const uint32_t w = blockIdx.x, j = threadIdx.x;
-    if (w >= sets) return;
-    XYZZ<F> acc = XYZZ<F>::zero();
-    if (nb == 0) {  // a single bucket (c = 1 never happens; kept for completeness)
-        if (j == 0) acc = C[w];
-    } else {
-        const XYZZ<F> *c2 = C + (size_t)w * 2;
-        if (j + 1 < nb) acc = D[(size_t)w * (nb - 1) + j];        // T_j
-        else if (j + 1 == nb) acc = c2[1];                        // T_(nb-1) = the odd entry of the last C
-        else if (j == nb) { acc = c2[0]; acc.add(c2[1]); }        // R
-        if (j < nb) for (uint32_t d = 0; d < j; d++) acc.dbl();
+    const uint32_t w = blockIdx.x, j = threadIdx.x >> 1;
+    const XYZZ<F> *c2 = C + (size_t)w * 2;
+    const XYZZ<F> *src = nullptr;
+    if (j + 1 < nb) src = D + (size_t)w * (nb - 1) + j;  // T_j
+    else if (j + 1 == nb || j == nb) src = c2 + 1;        // T_(nb-1) = the odd entry of the last C; R = C_0 + C_1 starts from C_1 too
+    PairXYZZ<F> acc = src ? PairXYZZ<F>::load(src) : PairXYZZ<F>::zero();
+    {
+        const PairXYZZ<F> c0 = j == nb ? PairXYZZ<F>::load(c2) : PairXYZZ<F>::zero();
+        acc.add(c0);  // only the R pair adds something
     }
-    sm[j] = acc;
+    for (uint32_t d = 0; d + 1 < nb; d++) {  // uniform trip count: the shuffles inside need every lane
+        PairXYZZ<F> t = acc;
+        t.dbl();
+        const bool mine = j < nb && d < j;
+        acc.a = lane_select(mine, t.a, acc.a);
+        acc.b = lane_select(mine, t.b, acc.b);
+    }
+    acc.store(&sm[j]);
     __syncthreads();
     for (uint32_t stride = 16; stride > 0; stride >>= 1) {
-        if (j < stride) {
-            XYZZ<F> t = sm[j];
-            t.add(sm[j + stride]);
-            sm[j] = t;
-        }
+        const bool on = j < stride;
+        PairXYZZ<F> x = on ? PairXYZZ<F>::load(&sm[j]) : PairXYZZ<F>::zero();
+        const PairXYZZ<F> y = on ? PairXYZZ<F>::load(&sm[j + stride]) : PairXYZZ<F>::zero();
+        x.add(y);
+        __syncthreads();
+        if (on) x.store(&sm[j]);
         __syncthreads();
     }
     if (j == 0) {
-        outR[w] = sm[0];
-        outA[w] = XYZZ<F>::zero();
+        PairXYZZ<F>::load(&sm[0]).store(&outR[w]);
+        PairXYZZ<F>::zero().store(&outA[w]);
     }
 }
 
@@ -607,13 +619,13 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     for (uint32_t step = 0; m > 2; step++, m >>= 1) {
         const size_t threads = (size_t)bw * ((m >> 1) + (size_t)(step + 1) * (m >> 2));
         XYZZ<F> *cout = lc[step & 1], *dout = ld[step & 1];
-        k_msm_ladder_step<F><<<(unsigned)((threads + 63) / 64), 64, 0, st>>>(cin, din, m, step, bw, cout, dout);
+        k_msm_ladder_step<F><<<(unsigned)((2 * threads + 63) / 64), 64, 0, st>>>(cin, din, m, step, bw, cout, dout);
         ctx->launches++;
         cin = cout;
         din = dout;
     }
     XYZZ<F> *inR = (XYZZ<F> *)(ws + o_fr), *inA = (XYZZ<F> *)(ws + o_fa);
-    k_msm_ladder_final<F><<<bw, 32, 0, st>>>(cin, din, sh.B >= 2 ? log_b : 0u, bw, inR, inA);
+    k_msm_ladder_final<F><<<bw, 64, 0, st>>>(cin, din, log_b, bw, inR, inA);
     ctx->launches++;
     k_msm_window_combine<F><<<K, 1, 0, st>>>(inR, inA, sh, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
     B200ZK_CUDA(ctx, cudaGetLastError());
