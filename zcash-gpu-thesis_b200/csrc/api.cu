@@ -77,6 +77,17 @@ int ctx_lanes(Ctx *ctx, int n) {
         b200zk_ctx *lane = nullptr;
         int rc = b200zk_init(ctx->device, &lane);
         if (rc) return set_error(ctx, rc, "could not create a prover lane");
+        if (ctx->lanes.size() >= 1) {
+            // lanes 1-3 carry the A, B-G1 and B-G2 multiexps of a proof, each followed by a serial piece of the assembly (a 255-bit
+            // scalar multiplication / the G2 chain): the longest chains of the call, so their blocks are scheduled first
+            int lo = 0, hi = 0;
+            cudaStream_t s = nullptr;
+            if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) == cudaSuccess) {
+                cudaStreamDestroy(lane->stream);
+                lane->stream = s;
+            }
+            cudaGetLastError();
+        }
         ctx->lanes.push_back(lane);
     }
     return B200ZK_OK;

@@ -154,6 +154,13 @@ __device__ __forceinline__ fq_t lane_swap(const fq_t &x) {  // the partner lane'
 }
 __device__ __forceinline__ fq2_t lane_swap(const fq2_t &x) { return {lane_swap(x.c0), lane_swap(x.c1)}; }
 
+// the exceptional cases go through out-of-line single-thread code on a point in local memory: nothing of it is inlined into
+// (or keeps registers alive across) the two-lane fast path
+template <class F>
+__device__ __noinline__ void xyzz_add_mixed_slow(XYZZ<F> *acc, const Affine<F> *p) { acc->add_mixed(*p, false); }
+template <class F>
+__device__ __noinline__ void xyzz_add_slow(XYZZ<F> *acc, const XYZZ<F> *o) { acc->add(*o); }
+
 template <class F>
 struct PairXYZZ {
     F a, b;  // role 0: (X, ZZ); role 1: (Y, ZZZ)
@@ -197,7 +204,7 @@ struct PairXYZZ {
             const F pc2 = lane_swap(c2);
             if (special) {
                 const Affine<F> p = r1 ? Affine<F>{pc2, c2} : Affine<F>{c2, pc2};
-                whole.add_mixed(p, false);
+                xyzz_add_mixed_slow(&whole, &p);
                 const PairXYZZ h = split(whole);
                 na = h.a;
                 nb = h.b;
@@ -232,7 +239,7 @@ struct PairXYZZ {
             XYZZ<F> whole = gather();
             const XYZZ<F> other = o.gather();
             if (special) {
-                whole.add(other);
+                xyzz_add_slow(&whole, &other);
                 const PairXYZZ h = split(whole);
                 na = h.a;
                 nb = h.b;

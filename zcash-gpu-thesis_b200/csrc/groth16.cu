@@ -25,99 +25,149 @@ namespace b200zk {
 // cursor starting right after the inputs (groth16/mod.rs:456-481); only their sums are used (prover.rs:339-347), so each
 // pair is one multiexp over inputs ++ aux with the concatenated density map.
 
-// scal[0] = r, scal[1] = s  (canonical FrRepr, 8 u32 each)
-// block 0: T = r * delta_g1 (table), g_a = T + alpha_g1 + a_in + a_aux ; B1 = beta_g1 + b1_in + b1_aux
-// block 1: T = s * delta_g2 (table), g_b = T + beta_g2 + b2_in + b2_aux  -> affine
+// All assembly kernels run on lane PAIRS (ec.cuh PairXYZZ: lane 0 holds (X, ZZ), lane 1 holds (Y, ZZZ)): they are chains of
+// dependent point operations in a handful of threads, i.e. pure latency, and the pair halves it.
+// scal[16 k ..] = r_k (8 words), s_k (8 words), canonical FrRepr.
+
+// sum of the 32 pairs' points of a 64-thread block (shared-memory tree); the result is valid in pair 0
 template <class F>
-__device__ void table_mul_warp(const XYZZ<F> *table, const uint32_t *scalar, XYZZ<F> *sm, XYZZ<F> &out) {
-    const uint32_t j = threadIdx.x;  // 32 threads, one 8-bit window each
-    uint32_t d = (scalar[j >> 2] >> (8 * (j & 3))) & 0xff;
-    sm[j] = d ? table[(size_t)j * 255 + d - 1] : XYZZ<F>::zero();
+__device__ PairXYZZ<F> pair_block_sum32(PairXYZZ<F> acc, XYZZ<F> *sm) {
+    const uint32_t j = threadIdx.x >> 1;
+    acc.store(&sm[j]);
     __syncthreads();
     for (uint32_t stride = 16; stride > 0; stride >>= 1) {
-        if (j < stride) {
-            XYZZ<F> t = sm[j];
-            t.add(sm[j + stride]);
-            sm[j] = t;
-        }
+        const bool on = j < stride;
+        PairXYZZ<F> x = on ? PairXYZZ<F>::load(&sm[j]) : PairXYZZ<F>::zero();
+        const PairXYZZ<F> y = on ? PairXYZZ<F>::load(&sm[j + stride]) : PairXYZZ<F>::zero();
+        x.add(y);
+        __syncthreads();
+        if (on) x.store(&sm[j]);
         __syncthreads();
     }
-    out = sm[0];
+    return PairXYZZ<F>::load(&sm[0]);
 }
+// T = scalar * (the point whose 8-bit window table is `table`: 32 windows x 255 multiples, built once per CRS): pair j looks up
+// window j, the block adds the 32 entries
+template <class F>
+__device__ PairXYZZ<F> pair_table_mul(const XYZZ<F> *table, const uint32_t *scalar, XYZZ<F> *sm) {
+    const uint32_t j = threadIdx.x >> 1;  // 64 threads, one 8-bit window per pair
+    const uint32_t d = (scalar[j >> 2] >> (8 * (j & 3))) & 0xff;
+    const PairXYZZ<F> e = d ? PairXYZZ<F>::load(table + (size_t)j * 255 + d - 1) : PairXYZZ<F>::zero();
+    return pair_block_sum32<F>(e, sm);
+}
+// Jacobian (X, Y, Z) -> the pair's halves of (X, Y, Z^2, Z^3)
+template <class F>
+__device__ PairXYZZ<F> pair_from_jacobian(const Jacobian<F> *p, bool mine) {
+    const bool r1 = PairXYZZ<F>::role();
+    const F z = mine ? p->z : F::zero();
+    const F zz = z.sqr();
+    const F zzz = zz * z;
+    PairXYZZ<F> out;
+    out.a = mine ? (r1 ? p->y : p->x) : F::zero();
+    out.b = r1 ? zzz : zz;
+    return out;
+}
+// affine (x, y) = (X / ZZ, Y / ZZZ): each lane inverts its own denominator (the reference's binary Euclid, fq.rs:849-903:
+// data-dependent loops, but no shuffle inside) -- lane 0 returns x, lane 1 returns y
+template <class F>
+__device__ F pair_to_affine_half(const PairXYZZ<F> &p) { return p.a * p.b.inverse_binary(); }
 
-// CurveProjective::mul_assign (ec.rs:528-552): MSB-first double and add over the 256 bits of a canonical FrRepr
-__device__ g1_jac_t jacobian_mul(const g1_jac_t &p, const uint32_t *k) {
-    g1_jac_t acc = g1_jac_t::zero();
-    bool found = false;
-    for (int i = 255; i >= 0; i--) {
-        bool bit = (k[i >> 5] >> (i & 31)) & 1;
-        if (found) jacobian_double(acc); else found = bit;
-        if (bit) jacobian_add(acc, p);
+// CurveProjective::mul_assign (ec.rs:528-552) on a lane pair: 4-bit fixed windows, MSB first.  `tab` (shared memory, 15 entries)
+// receives 1 P .. 15 P.  The scalar is uniform over the block, so the control flow is too.
+template <class F>
+__device__ PairXYZZ<F> pair_scalar_mul(const PairXYZZ<F> &p, const uint32_t *k, XYZZ<F> *tab) {
+    const bool mine = threadIdx.x < 2;
+    PairXYZZ<F> cur = p;
+    if (mine) cur.store(&tab[0]);
+    for (int i = 1; i < 15; i++) {  // i P -> (i + 1) P
+        if (i & 1) { PairXYZZ<F> h = mine ? PairXYZZ<F>::load(&tab[(i - 1) / 2]) : PairXYZZ<F>::zero(); h.dbl(); cur = h; }  // 2 m P = dbl(m P)
+        else cur.add(p);
+        if (mine) cur.store(&tab[i]);
+    }
+    PairXYZZ<F> acc = PairXYZZ<F>::zero();
+    for (int w = 63; w >= 0; w--) {
+        if (w != 63) { acc.dbl(); acc.dbl(); acc.dbl(); acc.dbl(); }
+        const uint32_t d = (k[w >> 3] >> (4 * (w & 7))) & 0xf;
+        if (d) {
+            const PairXYZZ<F> e = mine ? PairXYZZ<F>::load(&tab[d - 1]) : PairXYZZ<F>::zero();  // each lane reads back the halves it wrote itself
+            acc.add(e);
+        }
     }
     return acc;
 }
 
 // The assembly is cut along the multiexps it consumes, so each piece runs on the lane of its multiexp as soon as that one
-// is done (the two 256-bit variable-base products are ~2 ms of one thread each and would otherwise sit behind the join):
+// is done:
 //   k_proof_a  (after A):    g_a = r*delta_g1 (table) + alpha_g1 + A;  proof.a = affine(g_a);  sga = s * g_a
 //   k_proof_b1 (after B-G1): rb1 = r * (beta_g1 + B1)
 //   k_proof_b  (after B-G2): proof.b = affine(s*delta_g2 (table) + beta_g2 + B2)
 //   k_proof_c  (after all):  proof.c = affine(sga + rb1 + H + L)
-// One block per proof of the batch (blockIdx.x = k): scal[16 k ..] = r_k, s_k; every result array is indexed by k.
-__global__ void __launch_bounds__(32) k_proof_a(const g1_xyzz_t *table_d1, const uint32_t *scal, const g1_affine_t *vk_g1 /* alpha, beta, delta */,
-                                               bool alpha_inf, const g1_jac_t *res_a, g1_jac_t *sga, g1_affine_t *proof_a, uint8_t *inf_flags) {
+// One 64-thread block per proof of the batch (blockIdx.x = k); every result array is indexed by k.
+__global__ void __launch_bounds__(64) k_proof_a(const g1_xyzz_t *table_d1, const uint32_t *scal, const g1_affine_t *vk_g1 /* alpha, beta, delta */,
+                                               bool alpha_inf, const g1_jac_t *res_a, g1_xyzz_t *sga, g1_affine_t *proof_a, uint8_t *inf_flags) {
     __shared__ g1_xyzz_t sm[32];
     const uint32_t k = blockIdx.x;
+    const bool r1 = PairXYZZ<fq_t>::role();
     scal += 16 * k;
-    g1_xyzz_t t;
-    table_mul_warp<fq_t>(table_d1, scal, sm, t);
-    if (threadIdx.x != 0) return;
-    if (!alpha_inf) t.add_mixed(vk_g1[0], false);  // add_assign_mixed skips an identity operand (ec.rs:447-449)
-    t.add(g1_xyzz_t::from_jacobian(res_a[k]));
-    const g1_jac_t ga = t.to_jacobian();
-    g1_affine_t a;
-    bool ok = jacobian_to_affine_serial(ga, a);
-    proof_a[k] = a;
-    inf_flags[4 * k + 0] = ok ? 0 : 1;
-    sga[k] = jacobian_mul(ga, scal + 8);
+    PairXYZZ<fq_t> t = pair_table_mul<fq_t>(table_d1, scal, sm);
+    if (threadIdx.x >= 32) return;  // one warp goes on (its first pair does the work, the others run along on the identity)
+    const bool mine = threadIdx.x < 2;
+    if (!mine) t = PairXYZZ<fq_t>::zero();
+    const fq_t alpha_half = r1 ? vk_g1[0].y : vk_g1[0].x;
+    t.add_mixed(alpha_half, mine && !alpha_inf);  // add_assign_mixed skips an identity operand (ec.rs:447-449)
+    t.add(pair_from_jacobian<fq_t>(res_a + k, mine));
+    const bool zero = t.is_zero();
+    const fq_t h = pair_to_affine_half<fq_t>(t);
+    if (threadIdx.x == 0) { proof_a[k].x = zero ? fq_t::zero() : h; inf_flags[4 * k + 0] = zero ? 1 : 0; }
+    if (threadIdx.x == 1) proof_a[k].y = zero ? fq_t::one() : h;
+    __syncwarp();
+    const PairXYZZ<fq_t> prod = pair_scalar_mul<fq_t>(t, scal + 8, sm);
+    if (mine) prod.store(&sga[k]);
 }
 
-__global__ void __launch_bounds__(32) k_proof_b1(const uint32_t *scal, const g1_affine_t *vk_g1, bool beta_inf, const g1_jac_t *res_b1, g1_jac_t *rb1) {
-    if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_proof_b1(const uint32_t *scal, const g1_affine_t *vk_g1, bool beta_inf, const g1_jac_t *res_b1, g1_xyzz_t *rb1) {
+    __shared__ g1_xyzz_t sm[16];
     const uint32_t k = blockIdx.x;
-    g1_xyzz_t b1 = beta_inf ? g1_xyzz_t::zero() : g1_xyzz_t::from_affine(vk_g1[1]);
-    b1.add(g1_xyzz_t::from_jacobian(res_b1[k]));
-    rb1[k] = jacobian_mul(b1.to_jacobian(), scal + 16 * k);
+    const bool r1 = PairXYZZ<fq_t>::role(), mine = threadIdx.x < 2;
+    PairXYZZ<fq_t> b1 = PairXYZZ<fq_t>::zero();
+    const fq_t beta_half = r1 ? vk_g1[1].y : vk_g1[1].x;
+    b1.add_mixed(beta_half, mine && !beta_inf);
+    b1.add(pair_from_jacobian<fq_t>(res_b1 + k, mine));
+    const PairXYZZ<fq_t> prod = pair_scalar_mul<fq_t>(b1, scal + 16 * k, sm);
+    if (mine) prod.store(&rb1[k]);
 }
 
-__global__ void __launch_bounds__(32) k_proof_b(const g2_xyzz_t *table_d2, const uint32_t *scal, const g2_affine_t *vk_g2 /* beta, delta */,
+__global__ void __launch_bounds__(64) k_proof_b(const g2_xyzz_t *table_d2, const uint32_t *scal, const g2_affine_t *vk_g2 /* beta, delta */,
                                                bool beta_inf, const g2_jac_t *res_b2, g2_affine_t *proof_b, uint8_t *inf_flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     g2_xyzz_t *sm = reinterpret_cast<g2_xyzz_t *>(smem_raw);
     const uint32_t k = blockIdx.x;
-    g2_xyzz_t t;
-    table_mul_warp<fq2_t>(table_d2, scal + 16 * k + 8, sm, t);
-    if (threadIdx.x != 0) return;
-    if (!beta_inf) t.add_mixed(vk_g2[0], false);
-    t.add(g2_xyzz_t::from_jacobian(res_b2[k]));
-    g2_affine_t a;
-    bool ok = jacobian_to_affine_serial(t.to_jacobian(), a);
-    proof_b[k] = a;
-    inf_flags[4 * k + 1] = ok ? 0 : 1;
+    const bool r1 = PairXYZZ<fq2_t>::role();
+    PairXYZZ<fq2_t> t = pair_table_mul<fq2_t>(table_d2, scal + 16 * k + 8, sm);
+    if (threadIdx.x >= 32) return;
+    const bool mine = threadIdx.x < 2;
+    if (!mine) t = PairXYZZ<fq2_t>::zero();
+    const fq2_t beta_half = r1 ? vk_g2[0].y : vk_g2[0].x;
+    t.add_mixed(beta_half, mine && !beta_inf);
+    t.add(pair_from_jacobian<fq2_t>(res_b2 + k, mine));
+    const bool zero = t.is_zero();
+    const fq2_t h = pair_to_affine_half<fq2_t>(t);
+    if (threadIdx.x == 0) { proof_b[k].x = zero ? fq2_t::zero() : h; inf_flags[4 * k + 1] = zero ? 1 : 0; }
+    if (threadIdx.x == 1) proof_b[k].y = zero ? fq2_t::one() : h;
 }
 
-__global__ void __launch_bounds__(32) k_proof_c(const g1_jac_t *sga, const g1_jac_t *rb1, const g1_jac_t *res_h, const g1_jac_t *res_l,
+__global__ void __launch_bounds__(32) k_proof_c(const g1_xyzz_t *sga, const g1_xyzz_t *rb1, const g1_jac_t *res_h, const g1_jac_t *res_l,
                                                g1_affine_t *proof_c, uint8_t *inf_flags) {
-    if (threadIdx.x != 0) return;
     const uint32_t k = blockIdx.x;
-    g1_jac_t c = sga[k];
-    jacobian_add(c, rb1[k]);
-    jacobian_add(c, res_h[k]);
-    jacobian_add(c, res_l[k]);
-    g1_affine_t a;
-    bool ok = jacobian_to_affine_serial(c, a);
-    proof_c[k] = a;
-    inf_flags[4 * k + 2] = ok ? 0 : 1;
+    const bool mine = threadIdx.x < 2;
+    PairXYZZ<fq_t> c = mine ? PairXYZZ<fq_t>::load(&sga[k]) : PairXYZZ<fq_t>::zero();
+    c.add(mine ? PairXYZZ<fq_t>::load(&rb1[k]) : PairXYZZ<fq_t>::zero());
+    c.add(pair_from_jacobian<fq_t>(res_h + k, mine));
+    c.add(pair_from_jacobian<fq_t>(res_l + k, mine));
+    const bool zero = c.is_zero();
+    const fq_t h = pair_to_affine_half<fq_t>(c);
+    if (threadIdx.x == 0) { proof_c[k].x = zero ? fq_t::zero() : h; inf_flags[4 * k + 2] = zero ? 1 : 0; }
+    if (threadIdx.x == 1) proof_c[k].y = zero ? fq_t::one() : h;
 }
 
 static inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
@@ -175,7 +225,7 @@ int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_
     size_t o_da = take(K * n_all), o_db = take(K * n_all);   // [1..1] ++ a_aux_density ; b_input_density ++ b_aux_density
     size_t o_scal = take(K * 64), o_st = take(5 * K * 4);
     size_t o_rh = take(K * 144), o_rl = take(K * 144), o_ra = take(K * 144), o_rb1 = take(K * 144), o_rb2 = take(K * 288);
-    size_t o_sga = take(K * 144), o_rb1r = take(K * 144), o_pa = take(K * 96), o_pb = take(K * 192), o_pc = take(K * 96), o_inf = take(K * 4);
+    size_t o_sga = take(K * 192), o_rb1r = take(K * 192), o_pa = take(K * 96), o_pb = take(K * 192), o_pc = take(K * 96), o_inf = take(K * 4);
     int rc = ensure_scratch(ctx, &ctx->scratch3, &ctx->scratch3_bytes, off);
     if (rc) return rc;
     char *w = (char *)ctx->scratch3;
@@ -235,10 +285,14 @@ int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_
     if (n_lanes && (rc = ctx_lanes(ctx, n_lanes))) return rc;
     const g1_affine_t *vk1 = (const g1_affine_t *)crs->vk;
     const g2_affine_t *vk2 = (const g2_affine_t *)((const char *)crs->vk + 3 * 96);
-    g1_jac_t *sga = (g1_jac_t *)(w + o_sga), *rb1 = (g1_jac_t *)(w + o_rb1r);
+    g1_xyzz_t *sga = (g1_xyzz_t *)(w + o_sga), *rb1 = (g1_xyzz_t *)(w + o_rb1r);
     uint8_t *dinf = (uint8_t *)(w + o_inf);
     const uint32_t *scal = (const uint32_t *)(w + o_scal);
-    for (int j = 0; j < n_jobs; j++) {
+    // enqueue order = how early a lane gets its kernels: A first (a 255-bit scalar multiplication follows it), then the G2
+    // multiexp (the longest chain), B-G1 (another scalar multiplication), L, and H last (it waits for the H block anyway)
+    static const int order[n_jobs] = {2, 4, 3, 1, 0};
+    for (int oi = 0; oi < n_jobs; oi++) {
+        const int j = order[oi];
         // job 0 (H) stays on the main stream; job j >= 1 goes to lane (j - 1) mod n_lanes
         Ctx *on = (j == 0 || n_lanes == 0) ? ctx : ctx->lanes[(j - 1) % n_lanes];
         std::unique_lock<std::recursive_mutex> lk;
@@ -257,10 +311,10 @@ int groth16_prove_batch(Ctx *ctx, const Crs *crs, const ProveArgs *args, uint32_
         trace.mark(msm_names[j], on->stream);
         // the piece of the assembly (prover.rs:326-363) that only needs this multiexp
         if (j == 2)
-            k_proof_a<<<K, 32, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, crs->vk_inf[0] != 0, (const g1_jac_t *)(w + o_ra), sga, (g1_affine_t *)(w + o_pa), dinf);
+            k_proof_a<<<K, 64, 0, on->stream>>>((const g1_xyzz_t *)crs->table_delta_g1, scal, vk1, crs->vk_inf[0] != 0, (const g1_jac_t *)(w + o_ra), sga, (g1_affine_t *)(w + o_pa), dinf);
         if (j == 3) k_proof_b1<<<K, 32, 0, on->stream>>>(scal, vk1, crs->vk_inf[1] != 0, (const g1_jac_t *)(w + o_rb1), rb1);
         if (j == 4)
-            k_proof_b<<<K, 32, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, crs->vk_inf[2] != 0, (const g2_jac_t *)(w + o_rb2),
+            k_proof_b<<<K, 64, 32 * sizeof(g2_xyzz_t), on->stream>>>((const g2_xyzz_t *)crs->table_delta_g2, scal, vk2, crs->vk_inf[2] != 0, (const g2_jac_t *)(w + o_rb2),
                                                                     (g2_affine_t *)(w + o_pb), dinf);
         if (j >= 2) { on->launches++; trace.mark(piece_names[j], on->stream); }
         if (on != ctx) ctx->launches += on->launches - before;

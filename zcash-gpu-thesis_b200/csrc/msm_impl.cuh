@@ -304,6 +304,9 @@ template <class F>
 __global__ void __launch_bounds__(64) k_msm_combine_small(const uint32_t *__restrict__ split_list, const uint32_t *__restrict__ n_split,
                                                          const uint32_t *__restrict__ task_cnt, const uint32_t *__restrict__ task_off,
                                                          const XYZZ<F> *__restrict__ partials, XYZZ<F> *__restrict__ buckets) {
+    // one thread per split bucket: there are as many of them as buckets, so this kernel is throughput-bound and one thread per
+    // chain uses the multiplier best (lane pairs -- used by the reduction ladder below -- measured slower here and in the
+    // accumulation, at every size down to 2^12: G1 2^16 0.94 -> 1.08 ms, G2 61 300 points 2.8 -> 3.4 ms)
     const uint32_t total = n_split[0];
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += gridDim.x * blockDim.x) {
         const uint32_t b = split_list[s], cnt = task_cnt[b], off = task_off[b];
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(64) k_msm_combine_small(const uint32_t *__rest
         buckets[b] = acc;
     }
 }
-static constexpr uint32_t COMBINE_BIG_THREADS = 256;
+static constexpr uint32_t COMBINE_BIG_THREADS = 256;  // 128 lane pairs
 template <class F>
 __global__ void __launch_bounds__(COMBINE_BIG_THREADS) k_msm_combine_big(const uint32_t *__restrict__ split_list, const uint32_t *__restrict__ n_split,
                                                                         uint32_t n_buckets, const uint32_t *__restrict__ task_cnt,
@@ -320,22 +323,28 @@ __global__ void __launch_bounds__(COMBINE_BIG_THREADS) k_msm_combine_big(const u
                                                                         XYZZ<F> *__restrict__ buckets) {
     extern __shared__ __align__(16) unsigned char combine_smem[];
     XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(combine_smem);
-    const uint32_t total = n_split[1];
+    constexpr uint32_t PAIRS = COMBINE_BIG_THREADS / 2;
+    const uint32_t total = n_split[1], pj = threadIdx.x >> 1;
     for (uint32_t s = blockIdx.x; s < total; s += gridDim.x) {
         const uint32_t b = split_list[n_buckets - 1 - s], cnt = task_cnt[b], off = task_off[b];
-        XYZZ<F> acc = XYZZ<F>::zero();
-        for (uint32_t j = threadIdx.x; j < cnt; j += COMBINE_BIG_THREADS) acc.add(partials[off + j]);
-        sm[threadIdx.x] = acc;
+        PairXYZZ<F> acc = PairXYZZ<F>::zero();
+        for (uint32_t j0 = 0; j0 < cnt; j0 += PAIRS) {  // block-uniform trip count
+            const uint32_t j = j0 + pj;
+            const PairXYZZ<F> o = j < cnt ? PairXYZZ<F>::load(partials + off + j) : PairXYZZ<F>::zero();
+            acc.add(o);
+        }
+        acc.store(&sm[pj]);
         __syncthreads();
-        for (uint32_t stride = COMBINE_BIG_THREADS / 2; stride > 0; stride >>= 1) {
-            if (threadIdx.x < stride && threadIdx.x + stride < cnt) {
-                XYZZ<F> t = sm[threadIdx.x];
-                t.add(sm[threadIdx.x + stride]);
-                sm[threadIdx.x] = t;
-            }
+        for (uint32_t stride = PAIRS / 2; stride > 0; stride >>= 1) {
+            const bool on = pj < stride;
+            PairXYZZ<F> x = on ? PairXYZZ<F>::load(&sm[pj]) : PairXYZZ<F>::zero();
+            const PairXYZZ<F> y = on ? PairXYZZ<F>::load(&sm[pj + stride]) : PairXYZZ<F>::zero();
+            x.add(y);
+            __syncthreads();
+            if (on) x.store(&sm[pj]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) buckets[b] = sm[0];
+        if (pj == 0) PairXYZZ<F>::load(&sm[0]).store(buckets + b);
         __syncthreads();
     }
 }
@@ -428,26 +437,36 @@ __global__ void __launch_bounds__(64) k_msm_ladder_final(const XYZZ<F> *__restri
 
 // multiexp.rs:223-229: higher = 2^c * higher + this, from the top window down; then the status word.
 template <class F>
-__global__ void k_msm_window_combine(const XYZZ<F> *__restrict__ R, const XYZZ<F> *__restrict__ A, MsmShape sh, Jacobian<F> *__restrict__ out,
-                                     uint32_t *__restrict__ status, uint32_t *__restrict__ status_out) {
-    if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_msm_window_combine(const XYZZ<F> *__restrict__ R, const XYZZ<F> *__restrict__ A, MsmShape sh, Jacobian<F> *__restrict__ out,
+                                                          uint32_t *__restrict__ status, uint32_t *__restrict__ status_out) {
+    // one warp per multiexp of the batch; its first lane pair does the work (the other pairs run along on the identity)
     const uint32_t k = blockIdx.x;  // multiexp of the batch: its bucket sets are [k * sets, (k + 1) * sets)
+    const bool mine = threadIdx.x < 2;
     R += (size_t)k * sh.sets;
     A += (size_t)k * sh.sets;
-    XYZZ<F> acc = XYZZ<F>::zero();
+    PairXYZZ<F> acc = PairXYZZ<F>::zero();
     for (uint32_t w = sh.sets; w-- > 0;) {
-        for (uint32_t d = 0; d < sh.c; d++) acc.dbl();
-        XYZZ<F> t = A[w];
-        t.add(R[w]);
+        if (w + 1 < sh.sets) for (uint32_t d = 0; d < sh.c; d++) acc.dbl();
+        PairXYZZ<F> t = mine ? PairXYZZ<F>::load(A + w) : PairXYZZ<F>::zero();
+        const PairXYZZ<F> r = mine ? PairXYZZ<F>::load(R + w) : PairXYZZ<F>::zero();
+        t.add(r);
         acc.add(t);
     }
-    out[k] = acc.to_jacobian();
-    status += ST_PER_K + 3 * k;
-    uint32_t eof = status[0], ident = status[1];
-    uint32_t st = B200ZK_OK;
-    if (eof != NO_POS || ident != NO_POS) st = eof < ident ? B200ZK_ERR_UNEXPECTED_EOF : B200ZK_ERR_UNEXPECTED_IDENTITY;
-    status[2] = st;
-    if (status_out) status_out[k] = st;
+    const bool zero = acc.is_zero();
+    F zz;
+    const F h = acc.to_jacobian_half(&zz);  // X ZZ | Y ZZZ
+    if (threadIdx.x == 0) {
+        out[k].x = zero ? F::zero() : h;
+        out[k].z = zero ? F::zero() : zz;
+        status += ST_PER_K + 3 * k;
+        uint32_t eof = status[0], ident = status[1];
+        uint32_t st = B200ZK_OK;
+        if (eof != NO_POS || ident != NO_POS) st = eof < ident ? B200ZK_ERR_UNEXPECTED_EOF : B200ZK_ERR_UNEXPECTED_IDENTITY;
+        status[2] = st;
+        if (status_out) status_out[k] = st;
+    } else if (threadIdx.x == 1) {
+        out[k].y = zero ? F::one() : h;
+    }
 }
 
 template <class F>
@@ -627,7 +646,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     XYZZ<F> *inR = (XYZZ<F> *)(ws + o_fr), *inA = (XYZZ<F> *)(ws + o_fa);
     k_msm_ladder_final<F><<<bw, 64, 0, st>>>(cin, din, log_b, bw, inR, inA);
     ctx->launches++;
-    k_msm_window_combine<F><<<K, 1, 0, st>>>(inR, inA, sh, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
+    k_msm_window_combine<F><<<K, 32, 0, st>>>(inR, inA, sh, (Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
