@@ -302,6 +302,23 @@ int b200zk_groth16_prove_batch(b200zk_ctx *ctx, const b200zk_crs *crs, const b20
 int b200zk_groth16_prove_batch_bytes(b200zk_ctx *ctx, const b200zk_crs *crs, const b200zk_prove_input *proofs, size_t n_proofs, size_t n_constraints,
                                      size_t n_inputs, size_t n_aux, int lockstep, uint8_t *out_proofs);
 
+/* ---- groth16::verify_proof (bellman/src/groth16/verifier.rs:18-66) as a batch verifier on the device ----------------------
+ * The prover path needs no pairing; this closes the prove -> verify loop of the outer FFI (rustzcash.rs:1556-1601 verifies every
+ * proof it has just made).  b200zk_prepare_verifying_key = prepare_verifying_key (verifier.rs:18-33): e(alpha_g1, beta_g2), -gamma_g2,
+ * -delta_g2 and ic resident on the device.  b200zk_verify_proofs checks n proofs (affine Montgomery limbs as b200zk_groth16_prove
+ * returns them, 3 infinity flags each or NULL) against n x n_inputs public inputs (canonical FrRepr, WITHOUT the leading ONE):
+ * ok[i] = 1 iff e(A, B) = e(alpha, beta) e(sum_j input_j ic_j, gamma) e(C, delta).  n_inputs + 1 != ic.len() ->
+ * B200ZK_ERR_BAD_ARG (MalformedVerifyingKey, verifier.rs:41-43).  One thread block per proof.
+ * b200zk_pairing = Engine::pairing (pairing/src/lib.rs:86-96) for n independent pairs; out: n x 72 u64, the Fq12 value as
+ * c0.c0.c0, c0.c0.c1, c0.c1.c0 ... (6 u64 Montgomery limbs each) -- the canonical value the reference computes. */
+typedef struct b200zk_pvk b200zk_pvk;
+int b200zk_pairing(b200zk_ctx *ctx, const uint64_t *g1_xy, const uint8_t *g1_inf, const uint64_t *g2_xy, const uint8_t *g2_inf, size_t n, uint64_t *out_fq12);
+int b200zk_prepare_verifying_key(b200zk_ctx *ctx, const uint64_t alpha_g1[12], const uint64_t beta_g2[24], const uint64_t gamma_g2[24], const uint64_t delta_g2[24],
+                                 const uint64_t *ic, size_t n_ic, b200zk_pvk **out);
+void b200zk_pvk_free(b200zk_pvk *pvk);
+int b200zk_verify_proofs(b200zk_ctx *ctx, const b200zk_pvk *pvk, const uint64_t *proofs_a, const uint64_t *proofs_b, const uint64_t *proofs_c, const uint8_t *inf_flags,
+                         const uint64_t *public_inputs, size_t n_inputs, size_t n_proofs, uint8_t *ok);
+
 /* Per-kernel timing for the roofline report: when enabled, b200zk_multiexp(_dev) brackets its dominant kernel
  * (bucket accumulation) with CUDA events on the context's stream; read() synchronises and returns the summed
  * milliseconds and the number of launches since the last read. */

@@ -341,3 +341,32 @@ def test_fq2_kats():
         k = kat[name]
         args = [el(k["a"])] + ([el(k["b"])] if "b" in k else [])
         assert fn(*args) == el(k["out"]), name
+
+
+def test_generated_frobenius_constants():
+    """tools/gen_pairing_consts.py (the device verifier's Frobenius tables): the map sum a_m w^m -> sum conj^k(a_m) g_k^m w^m equals
+    plain powering by q^k in the oracle's Fq12 (pinned by the RELIC pairing KAT above), and the committed header is what the
+    generator writes."""
+    import random
+
+    from oracle import pairing as op
+    from oracle.fields import FQ_MODULUS as Q, Fq2
+    from tools.gen_pairing_consts import frobenius_constants
+
+    consts = frobenius_constants()
+    R = random.Random(11)
+    rnd2 = lambda: (R.randrange(Q), R.randrange(Q))
+    a = ((rnd2(), rnd2(), rnd2()), (rnd2(), rnd2(), rnd2()))
+    for k in (1, 2, 3):
+        conj = (lambda x: Fq2.frobenius(x)) if k & 1 else (lambda x: x)
+        g = consts[k]
+        want = op.f12_pow(a, Q ** k)
+        got = ((conj(a[0][0]), Fq2.mul(conj(a[0][1]), g[2]), Fq2.mul(conj(a[0][2]), g[4])),
+               (Fq2.mul(conj(a[1][0]), g[1]), Fq2.mul(conj(a[1][1]), g[3]), Fq2.mul(conj(a[1][2]), g[5])))
+        assert got == want, k
+    import subprocess, sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(here, "zcash-gpu-thesis_b200", "csrc", "pairing_consts.cuh")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(here, "tools", "gen_pairing_consts.py")], stdout=subprocess.DEVNULL)
+    assert open(path).read() == before

@@ -41,6 +41,11 @@ from .bellman import (  # noqa: F401
     multiexp_async,
     multiexp_batch,
     MultiWorker,
+    PreparedVerifyingKey,
+    pairing,
+    prepare_verifying_key,
+    verify_proof,
+    verify_proofs,
     ShardedBases,
     multi_plan,
     ntt_host,

@@ -95,6 +95,10 @@ SIGNATURES = {
     "b200zk_groth16_prove": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200zk_groth16_prove_batch": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _i, _vp, _vp, _vp, _vp]),
     "b200zk_groth16_prove_batch_bytes": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _sz, _i, _vp]),
+    "b200zk_pairing": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200zk_prepare_verifying_key": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "b200zk_pvk_free": (None, [_vp]),
+    "b200zk_verify_proofs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp]),
     "b200zk_launch_count": (C.c_ulonglong, [_vp, _i]),
     "b200zk_profile_enable": (_i, [_vp, _i]),
     "b200zk_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i)]),

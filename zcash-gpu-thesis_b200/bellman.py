@@ -926,6 +926,78 @@ def create_proof_bytes_from_assignments(worker, params: Parameters, assignments,
     return [out[192 * i:192 * (i + 1)].tobytes() for i in range(n)]
 
 
+# ------------------------------------------------------------------------------------------------------ verifier
+def pairing(worker, g1_xy, g2_xy, g1_inf=None, g2_inf=None):
+    """Engine::pairing (pairing/src/lib.rs:86-96) for n independent pairs on the device: (n, 72) uint64, the Fq12 values as
+    c0.c0.c0, c0.c0.c1, c0.c1.c0, ... Montgomery limbs (the order of the reference's known-answer literal)."""
+    p, q = _u64(g1_xy, 12), _u64(g2_xy, 24)
+    n = p.shape[0]
+    assert q.shape[0] == n
+    pi = None if g1_inf is None else np.ascontiguousarray(g1_inf, dtype=np.uint8)
+    qi = None if g2_inf is None else np.ascontiguousarray(g2_inf, dtype=np.uint8)
+    out = np.zeros((n, 72), dtype=np.uint64)
+    st = worker.lib.b200zk_pairing(worker.ctx, _ptr(p), _ptr(pi), _ptr(q), _ptr(qi), n, _ptr(out))
+    if st:
+        _raise(worker, st)
+    return out
+
+
+class PreparedVerifyingKey:
+    """groth16::PreparedVerifyingKey (groth16/mod.rs:384-393) made by prepare_verifying_key (verifier.rs:18-33), resident on the GPU"""
+
+    def __init__(self, worker, alpha_g1, beta_g2, gamma_g2, delta_g2, ic):
+        self.worker = worker
+        ic = _u64(ic, 12)
+        self.n_ic = ic.shape[0]
+        h = C.c_void_p()
+        st = worker.lib.b200zk_prepare_verifying_key(worker.ctx, _ptr(_u64(alpha_g1)), _ptr(_u64(beta_g2)), _ptr(_u64(gamma_g2)), _ptr(_u64(delta_g2)),
+                                                     _ptr(ic), self.n_ic, C.byref(h))
+        if st:
+            _raise(worker, st)
+        self.handle = h
+
+    def free(self):
+        if getattr(self, "handle", None) is not None and self.worker.ctx is not None:
+            self.worker.lib.b200zk_pvk_free(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def prepare_verifying_key(worker, vk) -> PreparedVerifyingKey:
+    """verifier.rs:18-33; `vk` is the dict Parameters.verifying_key() returns"""
+    return PreparedVerifyingKey(worker, vk["alpha_g1"][0], vk["beta_g2"][0], vk["gamma_g2"][0], vk["delta_g2"][0], vk["ic"])
+
+
+def verify_proofs(worker, pvk: PreparedVerifyingKey, proofs, public_inputs):
+    """groth16::verify_proof (verifier.rs:35-66) for a batch on the device: `proofs` is a sequence of Proof, `public_inputs` an
+    (n, n_inputs) sequence of ints (without the leading ONE).  Returns a list of bools.  Raises ValueError
+    (MalformedVerifyingKey) when the number of inputs does not fit the key."""
+    n = len(proofs)
+    if n == 0:
+        return []
+    a = np.stack([_u64(p.a) for p in proofs]).reshape(n, 12)
+    b = np.stack([_u64(p.b) for p in proofs]).reshape(n, 24)
+    c = np.stack([_u64(p.c) for p in proofs]).reshape(n, 12)
+    inf = np.array([[int(x) for x in p.inf] for p in proofs], dtype=np.uint8).reshape(n, 3)
+    n_in = len(public_inputs[0]) if n else 0
+    assert all(len(row) == n_in for row in public_inputs)
+    ins = np.array([[(int(v) % FR_MODULUS >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for v in row for j in range(4)] for row in public_inputs], dtype=np.uint64).reshape(n, max(n_in, 1) * 4 if n_in else 0)
+    ok = np.zeros(n, dtype=np.uint8)
+    st = worker.lib.b200zk_verify_proofs(worker.ctx, pvk.handle, _ptr(a), _ptr(b), _ptr(c), _ptr(inf), _ptr(ins) if n_in else None, n_in, n, _ptr(ok))
+    if st:
+        _raise(worker, st)
+    return [bool(x) for x in ok]
+
+
+def verify_proof(worker, pvk: PreparedVerifyingKey, proof, public_inputs) -> bool:
+    return verify_proofs(worker, pvk, [proof], [list(public_inputs)])[0]
+
+
 # ------------------------------------------------------------------------------------------- circuit-facing prover API
 ONE = ("in", 0)  # ConstraintSystem::one() (bellman/src/lib.rs): the first input variable
 
