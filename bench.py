@@ -519,6 +519,8 @@ def flat_secondary(extra):
     sp = extra.get("sapling_spend_proofs")
     if sp:
         out.update({"spend_proofs_per_s": sp["proofs_per_s"], "spend_single_proof_ms": sp["single_stream_ms_per_proof"]})
+    if extra.get("verify_proofs"):
+        out["verify_proofs_per_s"] = extra["verify_proofs"]["proofs_per_s"]
     for k, v in (extra.get("strong_scaling") or {}).items():
         out[f"strong_{k}_points_per_s"] = v["points_per_s"]
         out[f"strong_{k}_ms"] = v["ms_per_step"]
@@ -595,7 +597,57 @@ def bench_extra(env, rng):
     # the reference's largest circuit: Sprout JoinSplit on Groth16, 1 989 085 constraints -> m = 2^21
     out["sprout_joinsplit_shaped_proofs"] = bench_spend_proofs(env, rng, shape=synthetic.SPROUT_SHAPE)
     out["strong_scaling"] = bench_strong_scaling(env, rng)
+    out["verify_proofs"] = bench_verify(env)
     return out
+
+
+class _SquareChain:
+    """a small real circuit for the verifier measurement: x_(i+1) = x_i^2 + i over `rounds` constraints, the last value public"""
+
+    def __init__(self, x0, rounds):
+        self.x0, self.rounds = x0, rounds
+
+    def synthesize(self, cs):
+        p = FR_MODULUS
+        v = self.x0 % p
+        x = cs.alloc(lambda: v)
+        for i in range(self.rounds):
+            nv = (v * v + i) % p
+            y = cs.alloc_input(lambda nv=nv: nv) if i == self.rounds - 1 else cs.alloc(lambda nv=nv: nv)
+            cs.enforce([(x, 1)], [(x, 1)], [(y, 1), (("in", 0), -i)])
+            x, v = y, nv
+
+
+def bench_verify(env):
+    """groth16::verify_proof on the device (b200zk_verify_proofs): a real (small) circuit -- CRS generated on the GPU, proof made on
+    the GPU, accepted by the GPU verifier and rejected for a wrong public input -- then a batch of copies for the rate."""
+    w, zk, world = env.w, env.zk, env.world
+    circ = _SquareChain(3, 16)
+    asm = zk.KeypairAssembly()
+    asm.alloc_input()
+    _SquareChain(0, 16).synthesize(asm)
+    for i in range(asm.num_inputs):
+        asm.enforce([(("in", i), 1)], [], [])
+    gen = zk.generate_parameters(w, asm, gen_g1_limbs(), gen_g2_limbs(), 0x1111, 0x2222, 0x3333, 0x4444, 0x5555)
+    params = gen.to_device(w)
+    proof = zk.create_proof(w, circ, params, 0xABCDEF, 0x123456)
+    public = zk.synthesize(circ).input_assignment[1:]
+    pvk = zk.PreparedVerifyingKey(w, gen.alpha_g1, gen.beta_g2, gen.gamma_g2, gen.delta_g2, gen.ic)
+    if zk.verify_proofs(w, pvk, [proof, proof], [public, [(public[0] + 1) % FR_MODULUS]]) != [True, False]:
+        print(json.dumps({"error": "device verify_proof: accept / reject check failed"}))
+        sys.exit(1)
+    t0 = time.perf_counter()
+    zk.verify_proof(w, pvk, proof, public)
+    single_ms = (time.perf_counter() - t0) * 1e3
+    n = env_int("B200ZK_VERIFY_BATCH", 2048)
+    zk.verify_proofs(w, pvk, [proof] * n, [public] * n)
+    _line_up(world)
+    t0 = time.perf_counter()
+    ok = zk.verify_proofs(w, pvk, [proof] * n, [public] * n)
+    dt = _slowest_rank(time.perf_counter() - t0, world)
+    assert all(ok)
+    return {"proofs_per_s": world * n / dt, "batch": world * n, "single_proof_ms": single_ms, "public_inputs": len(public),
+            "note": "one thread block per proof: 3 Miller loops on 3 threads + the final exponentiation on one; host wall clock incl. copies"}
 
 
 def bench_strong_scaling(env, rng):

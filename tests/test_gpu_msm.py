@@ -304,26 +304,31 @@ def test_multiexp_futures_in_flight(worker):
         f.wait()
 
 
-def test_batched_affine_path_matches(worker, monkeypatch):
-    """The opt-in batched-affine accumulation (B200ZK_BA=1, msm_batched_affine.cuh) gives the same group element, including
-    duplicate bases (doubling), opposite points (identity) and oversized buckets."""
+def test_duplicates_and_cancelling_points_with_table(worker):
+    """Many duplicate bases with equal scalars (doubling branch), opposite points (identity) and oversized buckets (a third of the
+    exponents are 1) through the precomputed-table schedule, whose small-multiexp form cuts every chain into tasks and folds the
+    partial sums with the lane-pair kernels: == the oracle, with and without the table."""
     import zcash_gpu_thesis_b200 as zk
 
     n = 6000
     r = util.rng(1600)
     xy, ks = util.random_bases("g1", r, n)
     xy[1::7] = xy[0]  # many duplicates: doubling / cancelling pairs inside one bucket
+    neg = xy[2].copy()
+    neg[6:] = cref.field_vec("fq", "negate", neg[6:].reshape(1, 6)).reshape(-1)
+    xy[3::11] = neg   # and their opposites
     exps = util.random_fr_repr(r, n)
     exps[1::7] = exps[0]
+    exps[3::11] = exps[2]
     exps[r.random(n) < 0.3] = (1, 0, 0, 0)
-    bases = zk.Bases(worker, zk.G1, xy).precompute(0)
-    want = zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)
-    monkeypatch.setenv("B200ZK_BA", "1")
-    got = zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)
-    monkeypatch.delenv("B200ZK_BA")
-    assert np.array_equal(zk.into_affine(worker, zk.G1, got)[0], zk.into_affine(worker, zk.G1, want)[0])
     st, ref = cref.multiexp("g1", xy, exps)
-    assert st == 0 and np.array_equal(zk.into_affine(worker, zk.G1, got)[0][0], cref.into_affine("g1", ref)[0])
+    assert st == 0
+    want = cref.into_affine("g1", ref)[0]
+    bases = zk.Bases(worker, zk.G1, xy)
+    for rounds in range(2):
+        got = zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)
+        assert np.array_equal(zk.into_affine(worker, zk.G1, got)[0][0], want)
+        bases.precompute(0)
 
 
 @pytest.mark.parametrize("group,n,K,pre", [("g1", 0, 3, None), ("g1", 1, 2, None), ("g1", 777, 5, None), ("g1", 3000, 4, 0), ("g1", 1 << 13, 3, 12),
@@ -496,6 +501,28 @@ def test_two_devices_in_one_process(worker):
         st, want = cref.multiexp("g1", xy, exps[dev])
         want_aff, want_inf = cref.into_affine("g1", want)
         assert st == 0 and bool(got[dev][1][0]) == want_inf and np.array_equal(got[dev][0][0], want_aff)
+
+
+def test_non_canonical_scalar_is_reported(worker):
+    """The ABI takes any 4 x u64 as an exponent.  A canonical FrRepr (< r < 2^255) never carries out of the top window; a value with
+    bit 255 set can, when the window width divides 256: reported as a bad argument instead of silently dropping 2^256 P."""
+    import zcash_gpu_thesis_b200 as zk
+
+    r = util.rng(4700)
+    n = 300
+    xy, _ = util.random_bases("g1", r, n)
+    exps = util.random_fr_repr(r, n)
+    bases = zk.Bases(worker, zk.G1, xy)
+    bad = exps.copy()
+    bad[5] = (0xFFFFFFFFFFFFFFFF,) * 4
+    for c in (4, 8, 16):
+        worker.set_msm_window(c)
+        zk.multiexp(worker, (bases, 0), zk.FullDensity(), exps)
+        with pytest.raises(ValueError):
+            zk.multiexp(worker, (bases, 0), zk.FullDensity(), bad)
+    worker.set_msm_window(13)  # 20 windows of 13 bits = 260 bits: every 256-bit value fits
+    zk.multiexp(worker, (bases, 0), zk.FullDensity(), bad)
+    worker.set_msm_window(0)
 
 
 def _devices_for_group(worker, shards):

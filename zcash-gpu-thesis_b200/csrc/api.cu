@@ -445,10 +445,12 @@ int b200zk_multiexp(b200zk_ctx *ctx, const b200zk_bases *bases, size_t base_offs
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status, "UnexpectedIdentity: a base at infinity was consumed");
     if (status == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status, "IoError(UnexpectedEof): expected more bases from source");
+    if (status == B200ZK_ERR_BAD_ARG) return set_error(ctx, status, "an exponent is not a canonical FrRepr (it has 256 significant bits)");
     return B200ZK_OK;
 }
 
 static int status_to_error(b200zk_ctx *ctx, uint32_t status) {
+    if (status == B200ZK_ERR_BAD_ARG) return set_error(ctx, status, "an exponent is not a canonical FrRepr (it has 256 significant bits)");
     if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return set_error(ctx, status, "UnexpectedIdentity: a base at infinity was consumed");
     if (status == B200ZK_ERR_UNEXPECTED_EOF) return set_error(ctx, status, "IoError(UnexpectedEof): expected more bases from source");
     return B200ZK_OK;

@@ -28,10 +28,8 @@ struct Jacobian {  // ec.rs:20-24; identity <=> z == 0, canonical zero = (0, 1, 
 // a*b - c*d: for Fq one fused out-of-line body with a single reduction (fp.cuh mulsub_call), otherwise two products
 template <class F>
 __device__ __forceinline__ F mul_sub(const F &a, const F &b, const F &c, const F &d) { return a * b - c * d; }
-#ifndef B200ZK_NO_FUSED_MULSUB  // measured: G1 MSM 2^24 81.1 -> 79.7 ms
-template <>
+template <>  // measured: G1 MSM 2^24 81.1 -> 79.7 ms
 __device__ __forceinline__ fq_t mul_sub<fq_t>(const fq_t &a, const fq_t &b, const fq_t &c, const fq_t &d) { return fq_t::mulsub_call(a, b, c, d); }
-#endif
 
 template <class F>
 struct XYZZ {
@@ -72,8 +70,9 @@ struct XYZZ {
     // madd-2008-s with the exceptional cases of ec.rs:446-526 (self = identity, equal points, opposite points).
     // NEG: add -p instead (signed-digit buckets).
     __device__ __forceinline__ void add_mixed(const Affine<F> &p_in, bool neg) {
-        Affine<F> p = p_in;
-        if (neg) p.y = p.y.neg();
+        Affine<F> p;
+        p.x = p_in.x;
+        p.y = neg ? p_in.y.neg() : p_in.y;
         if (is_zero()) { *this = from_affine(p); return; }
         F u2 = p.x * zz;
         F s2 = p.y * zzz;

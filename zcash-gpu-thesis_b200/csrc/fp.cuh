@@ -256,65 +256,14 @@ struct __align__(16) Fp {
         for (int k = 1; k < M - 1; k++) T[M + k] = addc_cc(even[k], odd[k + 1]);
         T[2 * M - 1] = addc(even[M - 1], 0);
     }
-    // a * b (2N limbs, unreduced) with one level of Karatsuba: three N/2 x N/2 products (3 N^2 / 4 multiplier
-    // instructions instead of N^2) and ~90 additions, which go to the ALU pipe that the field product leaves idle:
-    // a0 b1 + a1 b0 = a0 b0 + a1 b1 + (a0 - a1)(b1 - b0)
-    __device__ __forceinline__ static void mul_wide_karatsuba(uint32_t *T, const uint32_t *a, const uint32_t *b) {
-        constexpr int H = N / 2;
-        uint32_t da[H], db[H], mid[2 * H], s[2 * H + 1];
-        mul_rows<H>(T, a, b);
-        mul_rows<H>(T + 2 * H, a + H, b + H);
-        da[0] = sub_cc(a[0], a[H]);
-#pragma unroll
-        for (int k = 1; k < H; k++) da[k] = subc_cc(a[k], a[H + k]);
-        const uint32_t ma = subc(0, 0);  // all ones when a0 < a1
-        db[0] = sub_cc(b[H], b[0]);
-#pragma unroll
-        for (int k = 1; k < H; k++) db[k] = subc_cc(b[H + k], b[k]);
-        const uint32_t mb = subc(0, 0);
-        // |da|, |db|: two's complement negation under the mask
-        da[0] = add_cc(da[0] ^ ma, ma & 1u);
-#pragma unroll
-        for (int k = 1; k < H - 1; k++) da[k] = addc_cc(da[k] ^ ma, 0);
-        da[H - 1] = addc(da[H - 1] ^ ma, 0);
-        db[0] = add_cc(db[0] ^ mb, mb & 1u);
-#pragma unroll
-        for (int k = 1; k < H - 1; k++) db[k] = addc_cc(db[k] ^ mb, 0);
-        db[H - 1] = addc(db[H - 1] ^ mb, 0);
-        mul_rows<H>(mid, da, db);
-        const uint32_t m = ma ^ mb;  // all ones when the middle product is negative
-        s[0] = add_cc(T[0], T[2 * H]);
-#pragma unroll
-        for (int k = 1; k < 2 * H; k++) s[k] = addc_cc(T[k], T[2 * H + k]);
-        s[2 * H] = addc(0, 0);
-        s[0] = add_cc(s[0], m & 1u);  // + (mid ^ m) + (m & 1), i.e. +mid or -mid, over 2H + 1 limbs
-#pragma unroll
-        for (int k = 1; k < 2 * H; k++) s[k] = addc_cc(s[k], 0);
-        s[2 * H] = addc(s[2 * H], 0);
-        s[0] = add_cc(s[0], mid[0] ^ m);
-#pragma unroll
-        for (int k = 1; k < 2 * H; k++) s[k] = addc_cc(s[k], mid[k] ^ m);
-        s[2 * H] = addc(s[2 * H], m);
-        T[H] = add_cc(T[H], s[0]);
-#pragma unroll
-        for (int k = 1; k <= 2 * H; k++) T[H + k] = addc_cc(T[H + k], s[k]);
-#pragma unroll
-        for (int k = 3 * H + 1; k < 2 * N - 1; k++) T[k] = addc_cc(T[k], 0);
-        T[2 * N - 1] = addc(T[2 * N - 1], 0);
-    }
-
     // fq.rs:910-963 mul_assign + fq.rs:1040-1123 mont_reduce  ->  a*b*R^-1 mod p, canonical
     __device__ __forceinline__ friend Fp operator*(const Fp &a, const Fp &b) {
-#ifdef B200ZK_INLINE_MUL
-        return mul_inline(a, b);
-#else
         return mul_call(a, b);
-#endif
     }
     // Out-of-line product: a fully inlined mixed add is ~100 KB of straight-line SASS and ncu showed
     // `no_instruction` (instruction-cache misses) as the top stall of the bucket-accumulation kernel.  One shared
     // ~10 KB function body keeps the hot loop inside the instruction cache; arguments and the result travel in
-    // registers (no stack traffic).  -DB200ZK_INLINE_MUL restores inlining for a translation unit.
+    // registers (no stack traffic).
     static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
     // Two independent products in one out-of-line body (used by the Fq2 product / squaring: one call instead of two,
     // 2 % on the G2 multiexp; pairing the products of the G1 point formulas the same way measured no gain).
@@ -340,13 +289,6 @@ struct __align__(16) Fp {
     struct Triple { Fp x, y, z; };
     static __device__ __noinline__ Triple mul3_call(Fp a, Fp b, Fp c, Fp d, Fp e, Fp f) { return {mul_inline(a, b), mul_inline(c, d), mul_inline(e, f)}; }
     __device__ __forceinline__ static Fp mul_inline(const Fp &a, const Fp &b) {
-#ifdef B200ZK_KARATSUBA
-        if (N == 12) {
-            uint32_t T[2 * N];
-            mul_wide_karatsuba(T, a.v, b.v);
-            return redc_wide(T);
-        }
-#endif
         uint32_t even[N], odd[N];
         // a's limbs interleave: even-indexed at a.v[0], a.v[2].. ; mul_n/cmad_n step by 2 from the pointer given
 #pragma unroll
@@ -366,11 +308,7 @@ struct __align__(16) Fp {
     // fq.rs:965-1002 square: the off-diagonal products a_i a_j (i < j) are formed once and doubled, 78 instead of 144
     // multiplier instructions for the product; then the same Montgomery rows as the product, without the a*b part.
     __device__ __forceinline__ Fp sqr() const {
-#ifdef B200ZK_INLINE_MUL
-        return sqr_inline(*this);
-#else
         return sqr_call(*this);
-#endif
     }
     static __device__ __noinline__ Fp sqr_call(Fp a) { return sqr_inline(a); }
     __device__ __forceinline__ static Fp sqr_inline(const Fp &a) {
@@ -442,47 +380,8 @@ struct __align__(16) Fp {
         final_sub(r.v);
         return r;
     }
-    // T = a * b, 2N limbs, not reduced (operands may be < 2p: used by the lazy-reduction Fq2 product)
-    __device__ __forceinline__ static void mul_wide(uint32_t *T, const uint32_t *a, const uint32_t *b) {
-        uint32_t E[2 * N], O[2 * N];  // E: even positions i + j; O[k] sits at limb k + 1 (odd positions)
-#pragma unroll
-        for (int k = 0; k < 2 * N; k++) { E[k] = 0; O[k] = 0; }
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            {   // j = i mod 2, +2, ...: even positions
-                const int j0 = i & 1;
-#pragma unroll
-                for (int j = j0; j < N; j += 2) {
-                    E[i + j] = j == j0 ? mad_lo_cc(a[j], b[i], E[i + j]) : madc_lo_cc(a[j], b[i], E[i + j]);
-                    E[i + j + 1] = madc_hi_cc(a[j], b[i], E[i + j + 1]);
-                }
-                const int last = i + (j0 + ((N - 1 - j0) / 2) * 2) + 1;
-#pragma unroll
-                for (int k = last + 1; k < 2 * N - 1; k++) E[k] = addc_cc(E[k], 0);
-                if (last + 1 <= 2 * N - 1) E[2 * N - 1] = addc(E[2 * N - 1], 0);
-            }
-            {   // odd positions
-                const int j0 = (i + 1) & 1;
-#pragma unroll
-                for (int j = j0; j < N; j += 2) {
-                    O[i + j - 1] = j == j0 ? mad_lo_cc(a[j], b[i], O[i + j - 1]) : madc_lo_cc(a[j], b[i], O[i + j - 1]);
-                    O[i + j] = madc_hi_cc(a[j], b[i], O[i + j]);
-                }
-                const int last = i + (j0 + ((N - 1 - j0) / 2) * 2);
-#pragma unroll
-                for (int k = last + 1; k < 2 * N - 1; k++) O[k] = addc_cc(O[k], 0);
-                if (last + 1 <= 2 * N - 1) O[2 * N - 1] = addc(O[2 * N - 1], 0);
-            }
-        }
-        T[0] = E[0];
-        T[1] = add_cc(E[1], O[0]);
-#pragma unroll
-        for (int k = 2; k < 2 * N - 1; k++) T[k] = addc_cc(E[k], O[k - 1]);
-        T[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
-    }
     // one reduction row: T += m p; T >>= 32 (roles of even / odd swap at the caller)
     __device__ __forceinline__ static void redc_row(uint32_t *even, uint32_t *odd, bool first) {
-#ifndef B200ZK_NO_FUSED_REDC_SHIFT
         if (!first && !(P::mod(0) == 1u && P::mod(1) == 0xffffffffu)) {
             // the two-limb shift of `odd` rides in the addend of its m * p products (as madc_n_rshift does for a * b):
             // 12 carry additions less per row than shifting first and multiplying after
@@ -496,7 +395,6 @@ struct __align__(16) Fp {
             odd[N - 1] = addc(odd[N - 1], 0);
             return;
         }
-#endif
         if (!first) {
             even[0] = add_cc(even[0], odd[1]);  // stray limb; the carry is absorbed while odd shifts down by two limbs
 #pragma unroll

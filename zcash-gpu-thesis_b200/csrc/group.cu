@@ -256,6 +256,7 @@ int b200zk_multi_job_wait(b200zk_group_job *job, uint64_t *out_jacobian) {
     if (e != cudaSuccess) return gerr(g, B200ZK_ERR_CUDA, cudaGetErrorString(e));
     if (status == B200ZK_ERR_UNEXPECTED_IDENTITY) return gerr(g, status, "UnexpectedIdentity: a base at infinity was consumed");
     if (status == B200ZK_ERR_UNEXPECTED_EOF) return gerr(g, status, "IoError(UnexpectedEof): expected more bases from source");
+    if (status == B200ZK_ERR_BAD_ARG) return gerr(g, status, "an exponent is not a canonical FrRepr (it has 256 significant bits)");
     return B200ZK_OK;
 }
 

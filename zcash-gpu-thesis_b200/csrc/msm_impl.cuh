@@ -25,7 +25,6 @@
 
 #include "ec.cuh"
 #include "internal.h"
-#include "msm_batched_affine.cuh"
 
 namespace b200zk {
 
@@ -120,6 +119,7 @@ struct MsmShape {
     uint32_t sets;     // bucket sets per multiexp: 1 with the precomputed table, W without
 };
 static constexpr uint32_t ST_PER_K = 8;  // offset of the per-multiexp status triples inside the status area
+static constexpr int ST_NONCANONICAL = 7;  // word 7 of the status area: some scalar of the call needs more than c W bits
 
 __device__ __forceinline__ uint32_t extract_bits(const uint32_t *s, uint32_t pos, uint32_t c) {
     uint32_t limb = pos >> 5, sh = pos & 31;
@@ -172,21 +172,17 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
             sorted[pos] = (uint32_t)(idx + (size_t)w * sh.pre_n) | (neg << 31);
         }
     }
+    // A carry out of the top window only happens for a scalar of 256 significant bits when c divides 256 (c W = 256): no canonical
+    // FrRepr (r < 2^255) gets here, but the ABI takes any 4 x u64, so the multiexp reports it instead of dropping 2^256 P silently
+    if (MODE == 0 && carry) status[ST_NONCANONICAL - (int)(ST_PER_K + 3 * k)] = 1u;
 }
 
 // ------------------------------------------------------------------------------------------------ bucket accumulation
-#ifndef B200ZK_ACC_MINBLOCKS
-#define B200ZK_ACC_MINBLOCKS 3
-#endif
-#ifndef B200ZK_ACC_MINBLOCKS_G2
-#define B200ZK_ACC_MINBLOCKS_G2 2
-#endif
-#ifndef B200ZK_ACC_THREADS_G2
-#define B200ZK_ACC_THREADS_G2 128
-#endif
+// resident blocks per SM the accumulation kernel is compiled for: G1 3 x 128 threads at 168 registers, G2 2 x 128 at 255
+// (measured: G2 with 12 warps at 168 registers 81.7 vs 77.8 ms at 2^22; 9-10 warps through __maxnreg__ 98.8 / 116 ms)
 template <class F> struct AccShape {
-    static constexpr unsigned THREADS = sizeof(F) > 48 ? B200ZK_ACC_THREADS_G2 : 128;
-    static constexpr unsigned MINBLOCKS = sizeof(F) > 48 ? B200ZK_ACC_MINBLOCKS_G2 : B200ZK_ACC_MINBLOCKS;
+    static constexpr unsigned THREADS = 128;
+    static constexpr unsigned MINBLOCKS = sizeof(F) > 48 ? 2 : 3;
 };
 // Oversized buckets (witness scalars are full of 0/1/small values: half of a Sapling witness lands in bucket 1 of
 // window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
@@ -283,13 +279,11 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MINBLOCKS) 
         // the next reference is read one addition ahead and its point is requested from HBM while this addition runs
         // (a prefetch costs no registers; the gather is a ~1 us dependent load in front of ~10 us of arithmetic)
         const uint32_t e_next = k + 1 < end ? sorted[k + 1] : 0u;
-#ifndef B200ZK_NO_POINT_PREFETCH
         if (k + 1 < end) {
             const char *nxt = reinterpret_cast<const char *>(bases + (e_next & 0x7fffffffu));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + sizeof(Affine<F>) - 1));
         }
-#endif
         Affine<F> p = bases[e & 0x7fffffffu];
         acc.add_mixed(p, (e >> 31) != 0);
         e = e_next;
@@ -462,6 +456,7 @@ __global__ void __launch_bounds__(32) k_msm_window_combine(const XYZZ<F> *__rest
         uint32_t eof = status[0], ident = status[1];
         uint32_t st = B200ZK_OK;
         if (eof != NO_POS || ident != NO_POS) st = eof < ident ? B200ZK_ERR_UNEXPECTED_EOF : B200ZK_ERR_UNEXPECTED_IDENTITY;
+        else if (status[ST_NONCANONICAL - (int)(ST_PER_K + 3 * k)]) st = B200ZK_ERR_BAD_ARG;
         status[2] = st;
         if (status_out) status_out[k] = st;
     } else if (threadIdx.x == 1) {
@@ -554,13 +549,6 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     size_t o_c0 = take((size_t)bw * half_b * sizeof(XYZZ<F>)), o_c1 = take((size_t)bw * quarter_b * sizeof(XYZZ<F>));
     size_t o_d0 = take((size_t)bw * quarter_b * sizeof(XYZZ<F>)), o_d1 = take((size_t)bw * quarter_b * sizeof(XYZZ<F>));
     size_t o_fr = take((size_t)bw * sizeof(XYZZ<F>)), o_fa = take((size_t)bw * sizeof(XYZZ<F>));
-    // batched-affine accumulation (msm_batched_affine.cuh): correct (the whole MSM suite passes with B200ZK_BA=1) but, as
-    // measured on B200 at 2^24 (accumulation 90.5 ms vs 76.7 ms for the XYZZ kernel), slower: its two passes over the
-    // points are bound by dependent gathers, not by the multiplier pipe.  Opt-in only.
-    bool use_ba = false;
-    if (const char *e = getenv("B200ZK_BA")) use_ba = e[0] == '1';
-    const size_t refs_bound = refs_max;
-    size_t o_ba = use_ba ? take(ba_workspace_bytes<F>(nbk, refs_bound)) : 0;
     int rc = ensure_scratch(ctx, &ctx->scratch2, &ctx->scratch2_bytes, off);
     if (rc) return rc;
     char *ws = (char *)ctx->scratch2;
@@ -574,6 +562,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     XYZZ<F> *lc[2] = {(XYZZ<F> *)(ws + o_c0), (XYZZ<F> *)(ws + o_c1)}, *ld[2] = {(XYZZ<F> *)(ws + o_d0), (XYZZ<F> *)(ws + o_d1)};
 
     B200ZK_CUDA(ctx, cudaMemsetAsync(status + ST_PER_K, 0xff, 3 * (size_t)K * sizeof(uint32_t), st));
+    B200ZK_CUDA(ctx, cudaMemsetAsync(status + ST_NONCANONICAL, 0, sizeof(uint32_t), st));
     if (n_exp == 0) {
         k_write_zero_point<F><<<K, 1, 0, st>>>((Jacobian<F> *)d_out_jac, status, (uint32_t *)d_status_out);
         B200ZK_CUDA(ctx, cudaGetLastError());
@@ -603,11 +592,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
     ctx->launches += passes - 1;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (ctx->prof_on) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); cudaEventRecord(pe0, st); }
-    if (use_ba) {
-        auto scan = [&](const uint32_t *in, size_t n, uint32_t *out, uint32_t *tmp) { return scan_u32<uint32_t>(st, in, n, out, nullptr, tmp); };
-        ctx->launches += 3;
-        if ((rc = ba_accumulate<F>(ctx, (const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk, refs_bound, buckets, ws + o_ba, scan))) return rc;
-    } else {
+    {
         uint32_t serial_max = SPLIT_SERIAL_MAX;
         if (const char *e = getenv("B200ZK_SPLIT_SERIAL_MAX")) serial_max = (uint32_t)atoi(e);
         uint32_t *n_split = status + 4;  // two counters: few-partial buckets, many-partial buckets
@@ -623,7 +608,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + AccShape<F>::THREADS - 1) / AccShape<F>::THREADS), AccShape<F>::THREADS, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
                                                                                       task_cnt, task_off, order, (uint32_t)max_tasks, buckets, partials);
         k_msm_combine_small<F><<<1024, 64, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
-        const size_t big_smem = COMBINE_BIG_THREADS * sizeof(XYZZ<F>);  // 48 KiB (G1) / 96 KiB (G2) of dynamic shared memory
+        const size_t big_smem = COMBINE_BIG_THREADS / 2 * sizeof(XYZZ<F>);  // one entry per lane pair: 24 KiB (G1) / 48 KiB (G2) of dynamic shared memory
         bool &opted_in = ctx->combine_smem_opt_in[sizeof(F) > 48 ? 1 : 0];
         if (!opted_in) {
             B200ZK_CUDA(ctx, cudaFuncSetAttribute(k_msm_combine_big<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
