@@ -26,6 +26,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/b200zk.h but not exported"
     # the ctypes table covers exactly the header
     assert sorted(zk._lib.SIGNATURES) == syms
+    # ... and so does the generated Rust -sys crate (bindings/rust/b200zk-sys/src/lib.rs, tools/gen_rust_bindings.py)
+    rust = open(os.path.join(ROOT, "bindings", "rust", "b200zk-sys", "src", "lib.rs")).read()
+    assert sorted(re.findall(r"pub fn (b200zk_[a-z0-9_]+)\(", rust)) == syms
+    # ... and the glue crate only calls entry points that exist
+    glue = open(os.path.join(ROOT, "bindings", "rust", "bellman-b200zk", "src", "lib.rs")).read()
+    assert set(re.findall(r"\b(b200zk_[a-z0-9_]+)\(", glue)) <= set(syms)
 
 
 def test_no_cpu_fallback_without_gpu():
