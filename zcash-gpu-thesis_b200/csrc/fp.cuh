@@ -170,15 +170,23 @@ struct __align__(16) Fp {
         for (int j = 2; j < N; j += 2) { acc[j] = madc_lo_cc(a[j], bi, acc[j]); acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 1]); }
     }
     // same with the modulus (immediates); `odd` selects limbs 1,3,5.. of p
+    // t0 = the limb m was derived from (m = -t0 mod 2^32 for Fr, whose M0 is 2^32 - 1)
     template <int ODD>
-    __device__ __forceinline__ static void cmad_mod(uint32_t *acc, uint32_t mi) {
+    __device__ __forceinline__ static void cmad_mod(uint32_t *acc, uint32_t mi, uint32_t t0) {
         if (P::mod(0) == 1u && P::mod(1) == 0xffffffffu) {
             // Fr: the two low limbs of r are 1 and 2^32 - 1, so their products with m need no multiplier:
-            //   m * 1 = m ;  m * (2^32 - 1) = (m - [m != 0]) * 2^32 + (2^32 - m)   (hi : lo)
-            uint32_t lo = ODD ? 0u - mi : mi;
-            uint32_t hi = ODD ? mi - (mi != 0u) : 0u;
-            acc[0] = add_cc(acc[0], lo);
-            acc[1] = addc_cc(acc[1], hi);
+            //   m * 1 = m ;  m * (2^32 - 1) = (m - [m != 0]) * 2^32 + (2^32 - m)   (hi : lo),  and 2^32 - m = t0 (no negation)
+            // c = [m != 0] = [t0 != 0] = min(t0, 1).  Even chain: t0 + m = c 2^32 exactly, so limb 0 (dropped by the shift) needs no
+            // addition and c goes straight into limb 1.
+            uint32_t c;
+            asm("min.u32 %0, %1, 1;" : "=r"(c) : "r"(t0));
+            if (ODD) {
+                acc[0] = add_cc(acc[0], t0);
+                acc[1] = addc_cc(acc[1], mi - c);
+            } else {
+                acc[0] = 0;
+                acc[1] = add_cc(acc[1], c);
+            }
         } else {
             acc[0] = mad_lo_cc(P::mod(ODD), mi, acc[0]);
             acc[1] = madc_hi_cc(P::mod(ODD), mi, acc[1]);
@@ -192,6 +200,15 @@ struct __align__(16) Fp {
         for (int j = 0; j < N - 2; j += 2) { acc[j] = madc_lo_cc(a[j], bi, acc[j + 2]); acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 3]); }
         acc[N - 2] = madc_lo_cc(a[N - 2], bi, 0);
         acc[N - 1] = madc_hi(a[N - 2], bi, 0);
+    }
+    // m = t0 * (-p^-1) mod 2^32.  Fq: M0 comes from constant memory (as an immediate ptxas strength-reduces the m * p_k products
+    // into slower forms).  Fr: M0 = 2^32 - 1, so m = -t0 -- an opaque ALU subtraction instead of a product on the multiplier pipe
+    // (the wide products keep their IMAD.WIDE.X form: 112 per Fr product in the SASS).
+    __device__ __forceinline__ static uint32_t mont_m(uint32_t t0) {
+        uint32_t mi;
+        if (P::N == 8) asm volatile("sub.u32 %0, 0, %1;" : "=r"(mi) : "r"(t0));
+        else mi = t0 * B200ZK_M0_RT[1];
+        return mi;
     }
     // One row: T += a*bi; T += m*p; T >>= 32 (the shift is implicit: the caller swaps `even` and `odd`).
     // Value represented: T = sum even[k] 2^(32k) + 2^32 * sum odd[k] 2^(32k).
@@ -212,9 +229,10 @@ struct __align__(16) Fp {
         }
         // M0 comes from constant memory: for Fr it is 2^32 - 1 and ptxas would otherwise rewrite m = -t0 and the
         // m * p_k products into negated IMAD.X / IMAD.HI pairs (6 cycles) instead of one IMAD.WIDE.X (4 cycles)
-        uint32_t mi = even[0] * B200ZK_M0_RT[P::N == 8 ? 0 : 1];
-        cmad_mod<1>(odd, mi);
-        cmad_mod<0>(even, mi);
+        const uint32_t t0 = even[0];
+        uint32_t mi = mont_m(t0);
+        cmad_mod<1>(odd, mi, t0);
+        cmad_mod<0>(even, mi, t0);
         odd[N - 1] = addc(odd[N - 1], 0);
     }
 
@@ -288,7 +306,13 @@ struct __align__(16) Fp {
     static __device__ __noinline__ Pair mul2_call(Fp a, Fp b, Fp c, Fp d) { return {mul_inline(a, b), mul_inline(c, d)}; }
     struct Triple { Fp x, y, z; };
     static __device__ __noinline__ Triple mul3_call(Fp a, Fp b, Fp c, Fp d, Fp e, Fp f) { return {mul_inline(a, b), mul_inline(c, d), mul_inline(e, f)}; }
-    __device__ __forceinline__ static Fp mul_inline(const Fp &a, const Fp &b) {
+    __device__ __forceinline__ static Fp mul_inline(const Fp &a, const Fp &b) { return mul_inline_t<true>(a, b); }
+    // CANONICAL = false: no final subtraction.  For a < p, b < 2p the result is < p (2p / R + 1) < 2p when 2p^2 < pR, true for Fr
+    // (r / 2^256 = 0.453): the NTT keeps its values in [0, 2r) between stages and pays one subtraction at the very end.
+    // The operand that may exceed p must be b, the one scanned limb by limb: a row leaves T < a + p, and the even/odd
+    // accumulator pair holds 2^32 (a + p) only while a + p < 2^(32N).
+    template <bool CANONICAL>
+    __device__ __forceinline__ static Fp mul_inline_t(const Fp &a, const Fp &b) {
         uint32_t even[N], odd[N];
         // a's limbs interleave: even-indexed at a.v[0], a.v[2].. ; mul_n/cmad_n step by 2 from the pointer given
 #pragma unroll
@@ -302,9 +326,42 @@ struct __align__(16) Fp {
 #pragma unroll
         for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(even[i], odd[i + 1]);
         r.v[N - 1] = addc(even[N - 1], 0);
-        final_sub(r.v);
+        if (CANONICAL) final_sub(r.v);
         return r;
     }
+    // ---- arithmetic on values in [0, 2p) (2p < 2^(32N) for both fields)
+    __device__ __host__ static constexpr uint32_t mod2(int i) { return (P::mod(i) << 1) | (i ? P::mod(i - 1) >> 31 : 0u); }
+    // (a + b) mod' 2p: a, b < 2p -> result < 2p.  The sum can pass 2^(32N): the carry joins the comparison.
+    __device__ __forceinline__ static Fp add_2p(const Fp &a, const Fp &b) {
+        Fp s;
+        uint32_t t[N];
+        s.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) s.v[i] = addc_cc(a.v[i], b.v[i]);
+        const uint32_t carry = addc(0, 0);
+        t[0] = sub_cc(s.v[0], mod2(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(s.v[i], mod2(i));
+        const uint32_t keep = subc(carry, 0) >> 31;  // 1 iff carry:s < 2p
+#pragma unroll
+        for (int i = 0; i < N; i++) s.v[i] = keep ? s.v[i] : t[i];
+        return s;
+    }
+    // (a - b) mod' 2p: a, b < 2p -> result < 2p
+    __device__ __forceinline__ static Fp sub_2p(const Fp &a, const Fp &b) {
+        Fp r;
+        r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+        const uint32_t borrow = subc(0, 0);
+        r.v[0] = add_cc(r.v[0], mod2(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(r.v[i], mod2(i) & borrow);
+        r.v[N - 1] = addc(r.v[N - 1], mod2(N - 1) & borrow);
+        return r;
+    }
+    // [0, 2p) -> [0, p)
+    __device__ __forceinline__ Fp canonical() const { Fp r = *this; final_sub(r.v); return r; }
     // fq.rs:965-1002 square: the off-diagonal products a_i a_j (i < j) are formed once and doubled, 78 instead of 144
     // multiplier instructions for the product; then the same Montgomery rows as the product, without the a*b part.
     __device__ __forceinline__ Fp sqr() const {
@@ -391,7 +448,7 @@ struct __align__(16) Fp {
             for (int j = 0; j < N - 2; j += 2) { odd[j] = madc_lo_cc(P::mod(j + 1), mi, odd[j + 2]); odd[j + 1] = madc_hi_cc(P::mod(j + 1), mi, odd[j + 3]); }
             odd[N - 2] = madc_lo_cc(P::mod(N - 1), mi, 0);
             odd[N - 1] = madc_hi(P::mod(N - 1), mi, 0);
-            cmad_mod<0>(even, mi);
+            cmad_mod<0>(even, mi, even[0]);
             odd[N - 1] = addc(odd[N - 1], 0);
             return;
         }
@@ -402,9 +459,10 @@ struct __align__(16) Fp {
             odd[N - 2] = addc(0, 0);
             odd[N - 1] = 0;
         }
-        uint32_t mi = even[0] * B200ZK_M0_RT[P::N == 8 ? 0 : 1];
-        cmad_mod<1>(odd, mi);
-        cmad_mod<0>(even, mi);
+        const uint32_t t0 = even[0];
+        uint32_t mi = mont_m(t0);
+        cmad_mod<1>(odd, mi, t0);
+        cmad_mod<0>(even, mi, t0);
         odd[N - 1] = addc(odd[N - 1], 0);
     }
 

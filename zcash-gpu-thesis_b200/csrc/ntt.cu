@@ -10,6 +10,7 @@
 // Twiddles omega^k are precomputed once per domain size and cached in the context.  Every butterfly is the
 // reference's (domain.rs:300-308): t = a[hi]*w; a[hi] = a[lo]-t; a[lo] += t, on canonical values, so the
 // output is bit-identical to serial_fft / parallel_fft.
+#include <cstdlib>
 #include "fp.cuh"
 #include "internal.h"
 
@@ -75,6 +76,7 @@ struct NttPass {
     const fr_t *scale;    // pre_scale: g^i, i < n;  post_scale == 2: g^-i / n, i < n;  post_scale == 1: &n^-1
     uint32_t log_n, s0;
     int pre_scale, post_scale;
+    int last;             // the last pass of the transform (k_ntt_pass4 delivers canonical values only there)
 };
 
 struct FrPair { fr_t lo, hi; };
@@ -230,6 +232,122 @@ __global__ void __launch_bounds__(NttShape<B, Q, XB>::THREADS, NttShape<B, Q, XB
     }
 }
 
+// ------------------------------------------------------------------------------------------------ radix-4 rounds, inlined
+// The large-transform pass: a thread owns FOUR elements and runs two stages on them (4 butterflies, 3 twiddles), fully inlined --
+// no call, so none of the ~38 register moves per butterfly that marshal operands into and out of an out-of-line body (all of
+// which ptxas splits between the ALU and the *multiplier* pipe as IMAD.MOV) -- and the rounds of a pass are a real loop, so the
+// kernel stays ~20 KB and inside the instruction cache.  The three twiddles of a round only depend on the thread: they are
+// requested right after the previous round's elements went to shared memory (their registers are free then) and arrive while the
+// block waits at the barrier, so no butterfly waits on a dependent table load.  Index conventions as in k_ntt_pass.
+template <int B, int Q>
+struct NttShape4 {
+    static constexpr int T = B + Q, TILE = 1 << T, THREADS = 1 << (T - 2);
+    static constexpr int K0 = (B & 1) ? 1 : 2, ROUNDS = (B + 1) / 2;  // an odd pass starts with a one-stage round
+    static constexpr int MINBLOCKS = (768 / THREADS) < 1 ? 1 : (768 / THREADS);  // 24 resident warps: 80 registers
+    static constexpr size_t SMEM = (size_t)2 * TILE * sizeof(uint4);
+};
+__device__ __forceinline__ uint32_t ntt_swz4(uint32_t e) { return e ^ ((e >> 2) & 4u); }  // bit 4 -> bit 2: conflict-free for every P >= 2
+template <int TILE>
+__device__ __forceinline__ fr_t ntt_sm_load4(const uint4 *sm, uint32_t e) {
+    const uint32_t w = ntt_swz4(e);
+    const uint4 lo = sm[w], hi = sm[TILE + w];
+    fr_t x;
+    x.v[0] = lo.x; x.v[1] = lo.y; x.v[2] = lo.z; x.v[3] = lo.w;
+    x.v[4] = hi.x; x.v[5] = hi.y; x.v[6] = hi.z; x.v[7] = hi.w;
+    return x;
+}
+template <int TILE>
+__device__ __forceinline__ void ntt_sm_store4(uint4 *sm, uint32_t e, const fr_t &x) {
+    const uint32_t w = ntt_swz4(e);
+    sm[w] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    sm[TILE + w] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+// Between the stages of a large transform the values live in [0, 2r) (2r < 2^256): the product of such a value with a canonical
+// twiddle is < 2r without its final subtraction (fp.cuh mul_inline_t<false>), sums and differences are folded back below 2r, and
+// the last round of the last pass subtracts r once more where needed.  Same residues, hence the same canonical outputs.
+__device__ __forceinline__ void ntt_bfly_inline(fr_t &lo, fr_t &hi, const fr_t &w) {
+    const fr_t t = fr_t::mul_inline_t<false>(w, hi);  // the canonical operand is the one multiplied as a whole (see fp.cuh)
+    hi = fr_t::sub_2p(lo, t);
+    lo = fr_t::add_2p(lo, t);
+}
+__device__ __forceinline__ void ntt_bfly_trivial(fr_t &lo, fr_t &hi) {
+    const fr_t t = hi;
+    hi = fr_t::sub_2p(lo, t);
+    lo = fr_t::add_2p(lo, t);
+}
+
+template <int B, int Q, bool FIRST>
+__global__ void __launch_bounds__(NttShape4<B, Q>::THREADS, NttShape4<B, Q>::MINBLOCKS) k_ntt_pass4(NttPass p) {
+    typedef NttShape4<B, Q> S;
+    extern __shared__ __align__(16) uint4 ntt_sm[];
+    const uint32_t t = threadIdx.x, tile = blockIdx.x;
+    const uint32_t log_n = p.log_n, s0 = FIRST ? 0u : p.s0;
+    const uint32_t mid = FIRST ? 0u : tile & ((1u << (s0 - Q)) - 1u), high = FIRST ? 0u : tile >> (s0 - Q);
+    auto gidx = [&](uint32_t e) -> uint32_t {
+        const uint32_t v = e >> Q, col = e & ((1u << Q) - 1u);
+        if (FIRST) return (Q ? col << (log_n - Q) : 0u) | (tile << B) | v;
+        return (high << (s0 + B)) | (v << s0) | (mid << Q) | col;
+    };
+    const fr_t *__restrict__ tw = p.tw;
+    fr_t x[4];
+    fr_t w0, w1, w2;
+#pragma unroll 1
+    for (int r = 0; r < S::ROUNDS; r++) {
+        const uint32_t P = (uint32_t)Q + (r == 0 ? 0u : (uint32_t)(S::K0 + 2 * (r - 1)));
+        const uint32_t e0 = ((t >> P) << (P + 2)) | (t & ((1u << P) - 1u));
+        const uint32_t sb = s0 + P - (uint32_t)Q;
+        const bool two = r > 0 || S::K0 == 2;
+        const bool trivial = FIRST && r == 0;  // omega^0 everywhere in stage 0, and for the pair (0, 2) in stage 1
+        const uint32_t idx0 = sb == 0 ? 0u : (gidx(e0) & ((1u << sb) - 1u)) << (log_n - 1 - sb);
+        if (!trivial) {
+            w0 = tw[idx0];
+            if (two) w1 = tw[idx0 >> 1];
+        }
+        if (two) w2 = tw[(idx0 >> 1) + (1u << (log_n - 2))];
+        if (r == 0) {
+#pragma unroll
+            for (int xi = 0; xi < 4; xi++) {
+                const uint32_t g = gidx(e0 | ((uint32_t)xi << P));
+                const uint32_t src = FIRST ? __brev(g) >> (32 - log_n) : g;
+                x[xi] = p.in[src];
+                if (FIRST && p.pre_scale) x[xi] = ntt_mul_call(x[xi], p.scale[src]);
+            }
+        } else {
+            __syncthreads();
+#pragma unroll
+            for (int xi = 0; xi < 4; xi++) x[xi] = ntt_sm_load4<S::TILE>(ntt_sm, e0 | ((uint32_t)xi << P));
+        }
+        if (trivial) {
+            ntt_bfly_trivial(x[0], x[1]);
+            ntt_bfly_trivial(x[2], x[3]);
+            if (two) {
+                ntt_bfly_trivial(x[0], x[2]);
+                ntt_bfly_inline(x[1], x[3], w2);
+            }
+        } else {
+            ntt_bfly_inline(x[0], x[1], w0);
+            ntt_bfly_inline(x[2], x[3], w0);
+            if (two) {
+                ntt_bfly_inline(x[0], x[2], w1);
+                ntt_bfly_inline(x[1], x[3], w2);
+            }
+        }
+        if (r == S::ROUNDS - 1) {
+#pragma unroll
+            for (int xi = 0; xi < 4; xi++) {
+                const uint32_t g = gidx(e0 | ((uint32_t)xi << P));
+                if (p.post_scale == 1) x[xi] = ntt_mul_call(p.scale[0], x[xi]);        // (the product of a value < 2r is canonical)
+                else if (p.post_scale == 2) x[xi] = ntt_mul_call(p.scale[g], x[xi]);
+                else if (p.last) x[xi] = x[xi].canonical();
+                p.out[g] = x[xi];
+            }
+        } else {
+#pragma unroll
+            for (int xi = 0; xi < 4; xi++) ntt_sm_store4<S::TILE>(ntt_sm, e0 | ((uint32_t)xi << P), x[xi]);
+        }
+    }
+}
+
 // n <= 4: one thread, the reference's loop as is (bit reversal, log n stages; domain.rs:272-315) with the scalings around it
 __global__ void k_ntt_tiny(fr_t *a, const fr_t *tw, const fr_t *g_pow, const fr_t *gi_pow, const fr_t *consts, uint32_t log_n, int kind) {
     const uint32_t n = 1u << log_n;
@@ -352,8 +470,27 @@ static int ntt_launch(Ctx *ctx, const NttPass &p) {
     ctx->launches++;
     return B200ZK_OK;
 }
+template <int B, int Q, bool FIRST>
+static int ntt_launch4(Ctx *ctx, const NttPass &p) {
+    typedef NttShape4<B, Q> S;
+    static bool opted_in[64] = {};
+    if (S::SMEM > 48 * 1024 && ctx->device < 64 && !opted_in[ctx->device]) {
+        B200ZK_CUDA(ctx, cudaFuncSetAttribute(k_ntt_pass4<B, Q, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        opted_in[ctx->device] = true;
+    }
+    const unsigned tiles = (unsigned)(((size_t)1 << p.log_n) >> S::T);
+    k_ntt_pass4<B, Q, FIRST><<<tiles, S::THREADS, S::SMEM, ctx->stream>>>(p);
+    ctx->launches++;
+    return B200ZK_OK;
+}
 template <bool FIRST>
 static int ntt_dispatch(Ctx *ctx, const NttPass &p, uint32_t B, uint32_t Q, uint32_t XB) {
+    if (XB == 2 && Q == 2) {
+        if (B == 6) return ntt_launch4<6, 2, FIRST>(ctx, p);
+        if (B == 7) return ntt_launch4<7, 2, FIRST>(ctx, p);
+        if (B == 8) return ntt_launch4<8, 2, FIRST>(ctx, p);
+        if (B == 9) return ntt_launch4<9, 2, FIRST>(ctx, p);
+    }
 #define B200ZK_NTT_CASE(CB, CQ, CX) if (B == CB && Q == CQ && XB == CX) return ntt_launch<CB, CQ, CX, FIRST>(ctx, p);
     // large transforms: eight elements per thread, four columns
     B200ZK_NTT_CASE(6, 2, 3) B200ZK_NTT_CASE(7, 2, 3) B200ZK_NTT_CASE(8, 2, 3) B200ZK_NTT_CASE(9, 2, 3)
@@ -405,12 +542,15 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         p.s0 = s0;
         p.tw = tw;
         p.pre_scale = (ps == 0 && kind == B200ZK_COSET_FFT) ? 1 : 0;
+        p.last = ps + 1 == npass;
         p.post_scale = ps + 1 == npass ? (kind == B200ZK_IFFT ? 1 : kind == B200ZK_ICOSET_FFT ? 2 : 0) : 0;
         p.scale = p.pre_scale ? (const fr_t *)t->g_pow : p.post_scale == 2 ? (const fr_t *)t->gi_pow : (const fr_t *)t->consts + C_N_INV;
         p.in = src;
         fr_t *dst = src == A ? S : A;  // a pass reads one buffer and writes the other (a tile's outputs are not its inputs)
         p.out = dst;
-        st = ps == 0 ? ntt_dispatch<true>(ctx, p, B, Q, large ? 3 : 1) : ntt_dispatch<false>(ctx, p, B, Q, large ? 3 : 1);
+        static const int r4 = getenv("B200ZK_NTT_R4") ? atoi(getenv("B200ZK_NTT_R4")) : 1;
+        const uint32_t XB = large ? (r4 ? 2 : 3) : 1;
+        st = ps == 0 ? ntt_dispatch<true>(ctx, p, B, Q, XB) : ntt_dispatch<false>(ctx, p, B, Q, XB);
         if (st) return st;
         src = dst;
         s0 += B;
