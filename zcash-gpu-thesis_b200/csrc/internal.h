@@ -59,7 +59,7 @@ struct Ctx {
     struct JobSlot { void *dev = nullptr; size_t bytes = 0, o_res = 0; void *host_res = nullptr; cudaEvent_t copied = nullptr, done = nullptr; bool busy = false; };
     JobSlot slots[4];
     int window_override = 0;  // b200zk_set_msm_window
-    int ntt_large_from = 22;  // log2 size from which a transform uses the eight-elements-per-thread kernels (B200ZK_NTT_LARGE_FROM)
+    int ntt_large_from = 20;  // log2 size from which a transform uses the radix-4 kernels (k_ntt_pass4) (B200ZK_NTT_LARGE_FROM)
     unsigned long long launches = 0;  // kernels launched by this context (b200zk_launch_count)
     bool prof_on = false;        // bracket the dominant MSM kernel with events
     // lanes: child contexts on the same device (own stream + workspaces) on which one create_proof runs its independent

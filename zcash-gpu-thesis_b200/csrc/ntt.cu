@@ -55,18 +55,16 @@ __global__ void k_pow_table(fr_t *__restrict__ out, const fr_t *__restrict__ bas
     }
 }
 
-// ------------------------------------------------------------------------------------------------ the pass kernel
+// ------------------------------------------------------------------------------------------------ the pass kernels
 // One pass = B consecutive radix-2 DIT stages (bits [s0, s0 + B) of the element index) over tiles of 2^B coupled elements x 2^Q
-// independent columns.  A thread owns EIGHT elements in registers and runs up to three stages on them without touching shared
-// memory (a radix-8 butterfly network: 12 butterflies, 7 distinct twiddles); between such rounds the tile is regrouped through
-// shared memory.  Per pass of 8 stages that is 2 shared-memory round trips and 2 barriers instead of 8 + 8, and the first
-// round reads its elements straight from HBM / the last one writes them straight back.  Twiddles omega^k come from the
-// per-domain table (precomputed once): a round's addresses only depend on the thread, so they are prefetched into L1 before the
-// data arrives and each butterfly's twiddle load is an L1 hit.  The butterfly itself (t = hi * w; hi = lo - t; lo += t,
-// domain.rs:300-308) is one out-of-line body shared by all call sites (instruction-cache friendly, see fp.cuh).
+// independent columns.  A thread owns 2^XB elements in registers and runs XB stages on them without touching shared memory;
+// between such rounds the tile is regrouped (warp shuffles / shared memory).  The first round reads its elements straight from
+// HBM, the last one writes them straight back.  Twiddles omega^k come from the per-domain table (precomputed once).
+//   k_ntt_pass  (XB = 1): small, latency-bound transforms -- one butterfly per thread and stage, out-of-line butterfly body.
+//   k_ntt_pass4 (XB = 2): large, work-bound transforms -- radix-4 rounds, everything inlined (further down).
 //   FIRST pass: input gathered in bit-reversed order (domain.rs:286-295 folded into the loads: the columns are the TOP index
 //   bits, so the four columns of a tile are four ADJACENT source elements = one 128-byte line) and the twiddles of its first
-//   round are 1, omega^(n/4), omega^(n/8) ...: the products by 1 are skipped (x * 1 = x exactly, the output stays bit-identical).
+//   round are 1, omega^(n/4), ...: the products by 1 are skipped (x * 1 = x exactly, the output stays bit-identical).
 //   coset_fft / icoset_fft / ifft scalings: ONE product per element at the first load (g^i table) / the last store
 //   (g^-i / n table or the constant 1 / n).
 struct NttPass {
@@ -80,9 +78,7 @@ struct NttPass {
 };
 
 struct FrPair { fr_t lo, hi; };
-// The product inside is the fused operand-scanning Montgomery product of fp.cuh.  Measured alternatives at 2^24 (ms per fft):
-// this 3.92; everything inlined (no call, 170 KB of straight-line code per kernel) 4.28; schoolbook rows + separate reduction
-// 4.30; one-level Karatsuba (48 instead of 64 wide multiplies) 5.04; 12 instead of 16 resident warps (no spills) 4.02.
+// The product inside is the fused operand-scanning Montgomery product of fp.cuh.
 static __device__ __noinline__ FrPair ntt_bfly_call(fr_t lo, fr_t hi, fr_t w) {
     const fr_t t = fr_t::mul_inline(hi, w);
     return {lo + t, lo - t};
@@ -147,14 +143,13 @@ __device__ __forceinline__ void ntt_round(fr_t (&x)[1 << XB], const fr_t *__rest
     }
 }
 
-// XB = 3 (eight elements per thread) for large transforms; XB = 1 (one butterfly per thread and stage; the elements change hands
-// by warp shuffle while the partner is a lane of the same warp, through shared memory afterwards) for small ones, whose time
-// is the length of the serial chain of a thread, not the work
+// XB = 1: one butterfly per thread and stage; the elements change hands by warp shuffle while the partner is a lane of the same
+// warp, through shared memory afterwards -- for small transforms, whose time is the serial chain of a thread, not the work
 template <int B, int Q, int XB>
 struct NttShape {
     static constexpr int T = B + Q, TILE = 1 << T, THREADS = 1 << (T - XB);
     static constexpr int K0 = (B - 1) % XB + 1, ROUNDS = (B + XB - 1) / XB;  // the short round comes first: rounds of K0, XB, XB ... stages
-    static constexpr int WARPS = XB == 3 ? 16 : 32;  // resident warps per SM the register budget is set for (16 -> 128 registers)
+    static constexpr int WARPS = 32;  // resident warps per SM the register budget is set for
     static constexpr int MINBLOCKS = (WARPS * 32 / THREADS) < 1 ? 1 : (WARPS * 32 / THREADS);
     static constexpr size_t SMEM = ROUNDS > 1 ? (size_t)2 * TILE * sizeof(uint4) : 0;
 };
@@ -316,6 +311,14 @@ __global__ void __launch_bounds__(NttShape4<B, Q>::THREADS, NttShape4<B, Q>::MIN
             __syncthreads();
 #pragma unroll
             for (int xi = 0; xi < 4; xi++) x[xi] = ntt_sm_load4<S::TILE>(ntt_sm, e0 | ((uint32_t)xi << P));
+        }
+        if (r + 1 < S::ROUNDS) {  // the next round's twiddles travel to L1 while this round computes (no registers held)
+            const uint32_t Pn = (uint32_t)(Q + S::K0 + 2 * r), sbn = s0 + Pn - (uint32_t)Q;
+            const uint32_t e0n = ((t >> Pn) << (Pn + 2)) | (t & ((1u << Pn) - 1u));
+            const uint32_t idxn = (gidx(e0n) & ((1u << sbn) - 1u)) << (log_n - 1 - sbn);
+            ntt_prefetch(tw + idxn);
+            ntt_prefetch(tw + (idxn >> 1));
+            ntt_prefetch(tw + (idxn >> 1) + (1u << (log_n - 2)));
         }
         if (trivial) {
             ntt_bfly_trivial(x[0], x[1]);
@@ -492,8 +495,6 @@ static int ntt_dispatch(Ctx *ctx, const NttPass &p, uint32_t B, uint32_t Q, uint
         if (B == 9) return ntt_launch4<9, 2, FIRST>(ctx, p);
     }
 #define B200ZK_NTT_CASE(CB, CQ, CX) if (B == CB && Q == CQ && XB == CX) return ntt_launch<CB, CQ, CX, FIRST>(ctx, p);
-    // large transforms: eight elements per thread, four columns
-    B200ZK_NTT_CASE(6, 2, 3) B200ZK_NTT_CASE(7, 2, 3) B200ZK_NTT_CASE(8, 2, 3) B200ZK_NTT_CASE(9, 2, 3)
     // small transforms: two elements per thread
     B200ZK_NTT_CASE(5, 2, 1) B200ZK_NTT_CASE(6, 2, 1) B200ZK_NTT_CASE(7, 2, 1) B200ZK_NTT_CASE(8, 2, 1)
     B200ZK_NTT_CASE(5, 0, 1) B200ZK_NTT_CASE(6, 0, 1) B200ZK_NTT_CASE(7, 0, 1) B200ZK_NTT_CASE(8, 0, 1) B200ZK_NTT_CASE(9, 0, 1)
@@ -522,20 +523,29 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         B200ZK_CUDA(ctx, cudaGetLastError());
         return B200ZK_OK;
     }
-    // Large transforms (work-bound): passes of at most 9 stages, eight elements per thread, four adjacent columns per tile
-    // (128-byte runs in HBM).  Small ones (latency-bound: the time is the serial chain of one thread): the same passes
-    // with one butterfly per thread and stage, columns only while they leave two tiles per SM.
-    const bool large = log_n >= (uint32_t)ctx->ntt_large_from;
-    const uint32_t npass = (log_n + 8) / 9;
+    // Large transforms (work-bound): k_ntt_pass4, passes of 8 or 6 stages where possible (whole radix-4 rounds; an odd size gets
+    // one pass of 7), four adjacent columns per tile (128-byte runs in HBM).  Small ones (latency-bound: the time is the serial
+    // chain of one thread): k_ntt_pass with one butterfly per thread and stage, passes of at most 9 stages, columns only while
+    // they leave two tiles per SM.
+    const bool large = log_n >= (uint32_t)ctx->ntt_large_from && log_n >= 12;
+    uint32_t npass = (log_n + 8) / 9, Bs[8];
+    for (uint32_t ps = 0; ps < npass; ps++) Bs[ps] = log_n / npass + (ps < log_n % npass ? 1 : 0);
+    if (large && 6 * ((log_n + 7) / 8) <= log_n) {
+        npass = (log_n + 7) / 8;
+        uint32_t rem = log_n - 6 * npass;
+        for (uint32_t ps = 0; ps < npass; ps++) Bs[ps] = 6;
+        if (rem & 1) { Bs[0] = 7; rem--; }
+        for (uint32_t ps = (Bs[0] == 7 ? 1 : 0); ps < npass && rem >= 2; ps++) { Bs[ps] = 8; rem -= 2; }
+        if (rem >= 2) { Bs[0] += 2; rem -= 2; }  // (7 -> 9; not reached for log_n <= 30)
+    }
     st = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, n * sizeof(fr_t));
     if (st) return st;
     fr_t *S = (fr_t *)ctx->scratch;
-    const uint32_t base = log_n / npass, extra = log_n % npass;
     uint32_t s0 = 0;
     const fr_t *src = A;
     for (uint32_t ps = 0; ps < npass; ps++) {
         NttPass p;
-        const uint32_t B = base + (ps < extra ? 1 : 0);
+        const uint32_t B = Bs[ps];
         uint32_t Q = npass == 1 ? 0 : 2;
         if (!large && Q && ((n >> (B + Q)) < (size_t)2 * ctx->sm_count || B + Q > 10)) Q = 0;
         p.log_n = log_n;
@@ -546,10 +556,12 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         p.post_scale = ps + 1 == npass ? (kind == B200ZK_IFFT ? 1 : kind == B200ZK_ICOSET_FFT ? 2 : 0) : 0;
         p.scale = p.pre_scale ? (const fr_t *)t->g_pow : p.post_scale == 2 ? (const fr_t *)t->gi_pow : (const fr_t *)t->consts + C_N_INV;
         p.in = src;
-        fr_t *dst = src == A ? S : A;  // a pass reads one buffer and writes the other (a tile's outputs are not its inputs)
+        // The first pass gathers in bit-reversed order, so it writes to the other buffer; every later pass reads and writes the
+        // same positions (a tile's reads all precede its first barrier, its writes follow the last), so the middle passes run in
+        // place in the scratch buffer and the last one delivers into the caller's vector: no copy for any number of passes.
+        fr_t *dst = ps == 0 ? S : ps + 1 == npass ? A : S;
         p.out = dst;
-        static const int r4 = getenv("B200ZK_NTT_R4") ? atoi(getenv("B200ZK_NTT_R4")) : 1;
-        const uint32_t XB = large ? (r4 ? 2 : 3) : 1;
+        const uint32_t XB = large ? 2 : 1;
         st = ps == 0 ? ntt_dispatch<true>(ctx, p, B, Q, XB) : ntt_dispatch<false>(ctx, p, B, Q, XB);
         if (st) return st;
         src = dst;
