@@ -279,18 +279,20 @@ int b200zk_bases_precompute(b200zk_ctx *ctx, b200zk_bases *bases, int window_bit
     if (!bases) return set_error(ctx, B200ZK_ERR_BAD_ARG, "null bases");
     USE_DEVICE(ctx);
     uint32_t c = (uint32_t)window_bits;
-    if (window_bits <= 0) {  // automatic: about log2(n) - 2, so that the single bucket set costs a few percent of the adds
+    if (window_bits <= 0) {
+        // Automatic.  Measured on B200 (G1 and G2, 2^16 ... 2^26, profiles/r02_msm_window_sweep.txt): what counts is the number
+        // of windows W = ceil(255 / c) (mixed adds per point) and a TOP window that is not nearly empty -- with 255 = (W - 1) c + t
+        // the 2^(t-1) buckets of the top window receive n / 2^(t-1) points each, and t = 2 or 3 (c = 18, 21, 23) costs 20-30 %.
+        // c = 16 / 20 / 22 / 24 leave t = 15 / 15 / 13 / 15.
         uint32_t lg = 0;
         while (((size_t)1 << (lg + 1)) <= bases->n) lg++;
-        // small n: c = log2 n keeps ~50 points per bucket and tens of thousands of buckets (threads) in flight;
-        // large n: the single bucket set must stay a few percent of the adds
-        c = lg < 19 ? lg : lg - 1;
+        c = lg <= 18 ? lg : lg <= 21 ? 20 : lg <= 25 ? 22 : 24;
         if (const char *e = getenv("B200ZK_PRE_DELTA")) c = lg - (uint32_t)atoi(e);
         if (c < 8) c = 8;
-        if (c > 22) c = 22;
         // 255 = 15 x 17: with c = 15 or 17 the scalar fills its windows exactly and the signed-digit carry of the last one lands in
         // an extra window whose only bucket (digit 1) then receives half of all the points; one bit more avoids that
         if (255 % c == 0) c++;
+        if (const char *e = getenv("B200ZK_PRE_C")) c = (uint32_t)atoi(e);
     }
     return msm_precompute(ctx, bases, c);
 }
