@@ -302,6 +302,27 @@ struct __align__(16) Fp {
         T[2 * N - 1] = addc(T[2 * N - 1], U[2 * N - 1]);
         return redc_wide(T);
     }
+    // a*b + c*d with ONE Montgomery reduction, for operands up to p (not only below it): T <= 2 p^2 < p R.  The lane-split Fq2
+    // product (fq2.cuh fq2h_t) is such a sum on either lane -- a0 b0 + (p - a1) b1 and a0 b1 + a1 b0.
+    static __device__ __noinline__ Fp muladd2_call(Fp a, Fp b, Fp c, Fp d) {
+        uint32_t T[2 * N], U[2 * N];
+        mul_rows<N>(U, c.v, d.v);
+        mul_rows<N>(T, a.v, b.v);
+        T[0] = add_cc(T[0], U[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N - 1; k++) T[k] = addc_cc(T[k], U[k]);
+        T[2 * N - 1] = addc(T[2 * N - 1], U[2 * N - 1]);
+        return redc_wide(T);
+    }
+    // p - a without the zero test: a value in (0, p] that stands for -a as an operand of muladd2_call
+    __device__ __forceinline__ Fp neg_raw() const {
+        Fp r;
+        r.v[0] = sub_cc(P::mod(0), v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = subc_cc(P::mod(i), v[i]);
+        r.v[N - 1] = subc(P::mod(N - 1), v[N - 1]);
+        return r;
+    }
     struct Pair { Fp x, y; };
     static __device__ __noinline__ Pair mul2_call(Fp a, Fp b, Fp c, Fp d) { return {mul_inline(a, b), mul_inline(c, d)}; }
     struct Triple { Fp x, y, z; };

@@ -45,4 +45,56 @@ struct fq2_t {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ one Fq2 element on a lane pair
+// fq2h_t is ONE component of an Fq2 element: the even lane of a pair holds c0, the odd lane c1 of the same element, and both
+// lanes run the same instruction stream.  Additions are componentwise (no traffic); a product needs the partner's operands
+// (2 x 12 warp shuffles) and is, on either lane, a sum of two Fq products under ONE reduction:
+//     even: c0 = a0 b0 + (q - a1) b1        odd: c1 = a0 b1 + a1 b0            (2 x 144 + 156 = 444 multiplier instructions per lane;
+// the single-thread Karatsuba product is 3 x 300 = 900), a square is one Fq product per lane ((a0 + a1)(a0 - a1) | (a1 + a1) a0).
+// An Fq2 point then needs half the registers per thread (the G2 bucket accumulation spilled at 255), and a dependent point
+// addition takes half the time.  Same field values, canonical per component, as fq2_t.
+// Every function must be called by both lanes of the pair together (the shuffles name exactly these two lanes).
+struct fq2h_t {
+    fq_t c;
+    __device__ __forceinline__ static unsigned role() { return threadIdx.x & 1u; }
+    __device__ __forceinline__ static unsigned pair_mask() { return 3u << (threadIdx.x & 30u); }
+    __device__ __forceinline__ static fq_t partner(const fq_t &v) {
+        fq_t r;
+#pragma unroll
+        for (int i = 0; i < fq_t::N; i++) r.v[i] = __shfl_xor_sync(pair_mask(), v.v[i], 1);
+        return r;
+    }
+    __device__ __forceinline__ static fq_t pick(bool first, const fq_t &a, const fq_t &b) {
+        fq_t r;
+#pragma unroll
+        for (int i = 0; i < fq_t::N; i++) r.v[i] = first ? a.v[i] : b.v[i];
+        return r;
+    }
+    __device__ __forceinline__ static fq2h_t zero() { return {fq_t::zero()}; }
+    __device__ __forceinline__ static fq2h_t one() { return {pick(role() == 0, fq_t::one(), fq_t::zero())}; }
+    __device__ __forceinline__ bool is_zero() const {
+        const int z = c.is_zero();
+        return z & __shfl_xor_sync(pair_mask(), z, 1);
+    }
+    __device__ __forceinline__ friend fq2h_t operator+(const fq2h_t &a, const fq2h_t &b) { return {a.c + b.c}; }
+    __device__ __forceinline__ friend fq2h_t operator-(const fq2h_t &a, const fq2h_t &b) { return {a.c - b.c}; }
+    __device__ __forceinline__ fq2h_t dbl() const { return {c.dbl()}; }
+    __device__ __forceinline__ fq2h_t neg() const { return {c.neg()}; }
+    __device__ __forceinline__ friend fq2h_t operator*(const fq2h_t &a, const fq2h_t &b) {
+        const bool odd = role() != 0;
+        const fq_t ap = partner(a.c), bp = partner(b.c);
+        // X * b_mine + Y * b_partner:  even (X, Y) = (a0, q - a1),  odd (X, Y) = (a0, a1) with b_mine = b1, b_partner = b0
+        const fq_t X = pick(odd, ap, a.c);
+        const fq_t Y = pick(odd, a.c, ap.neg_raw());
+        return {fq_t::muladd2_call(X, b.c, Y, bp)};
+    }
+    __device__ __forceinline__ fq2h_t sqr() const {
+        const bool odd = role() != 0;
+        const fq_t ap = partner(c);
+        const fq_t P = c + pick(odd, c, ap);      // even: a0 + a1      odd: a1 + a1
+        const fq_t Q = pick(odd, ap, c - ap);     // even: a0 - a1      odd: a0
+        return {fq_t::mul_call(P, Q)};
+    }
+};
+
 }  // namespace b200zk

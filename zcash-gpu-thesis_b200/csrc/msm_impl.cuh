@@ -291,6 +291,78 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MINBLOCKS) 
     *dst = acc;
 }
 
+// The same accumulation for G2 with TWO lanes per bucket chain: each lane holds one Fq component of every Fq2 coordinate (fq2h_t,
+// fq2.cuh).  Round 1 ran one thread per chain at 255 registers with a 1.5 KB stack frame (97 M local loads per 2^20 multiexp);
+// a lane of a pair needs about what a G1 thread needs.  Layout in memory is unchanged (x.c0 x.c1 y.c0 y.c1 | X Y ZZ ZZZ).
+struct AccPairShape {
+    static constexpr unsigned THREADS = 128, MINBLOCKS = 3;
+};
+static __global__ void __launch_bounds__(AccPairShape::THREADS, AccPairShape::MINBLOCKS)
+k_msm_accumulate_pair(const Affine<fq2_t> *__restrict__ bases, const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ offsets, uint32_t n_buckets,
+                      const uint32_t *__restrict__ task_cnt, const uint32_t *__restrict__ task_off, const uint32_t *__restrict__ order, uint32_t max_tasks,
+                      XYZZ<fq2_t> *__restrict__ buckets, XYZZ<fq2_t> *__restrict__ partials) {
+    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;  // both lanes of a pair take the same path everywhere below
+    const unsigned role = threadIdx.x & 1u;
+    uint32_t beg, end;
+    XYZZ<fq2_t> *dst;
+    if (t >= max_tasks) {
+        t -= max_tasks;
+        if (t >= n_buckets) return;
+        uint32_t b = order[t];
+        if (task_cnt[b]) return;
+        beg = offsets[b];
+        end = offsets[b + 1];
+        dst = buckets + b;
+    } else {
+        uint32_t task = t;
+        if (task >= task_off[n_buckets]) return;
+        uint32_t lo = 0, hi = n_buckets;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (task_off[mid] <= task) lo = mid; else hi = mid;
+        }
+        const uint32_t j = task - task_off[lo], tasks = task_off[lo + 1] - task_off[lo];
+        const uint32_t first = offsets[lo], cnt = offsets[lo + 1] - first;
+        beg = first + (uint32_t)(((uint64_t)cnt * j) / tasks);
+        end = first + (uint32_t)(((uint64_t)cnt * (j + 1)) / tasks);
+        dst = partials + task;
+    }
+    XYZZ<fq2h_t> acc = XYZZ<fq2h_t>::zero();
+    uint32_t e = beg < end ? sorted[beg] : 0u;
+    for (uint32_t k = beg; k < end; k++) {
+        const uint32_t e_next = k + 1 < end ? sorted[k + 1] : 0u;
+        if (k + 1 < end) {  // the 192-byte point spans two lines: one prefetch per lane
+            const char *nxt = reinterpret_cast<const char *>(bases + (e_next & 0x7fffffffu));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (role ? sizeof(Affine<fq2_t>) - 1 : 0)));
+        }
+        const fq_t *src = reinterpret_cast<const fq_t *>(bases + (e & 0x7fffffffu));
+        Affine<fq2h_t> p;
+        p.x.c = src[role];
+        p.y.c = src[2 + role];
+        acc.add_mixed(p, (e >> 31) != 0);
+        e = e_next;
+    }
+    fq_t *out = reinterpret_cast<fq_t *>(dst);
+    out[role] = acc.x.c;
+    out[2 + role] = acc.y.c;
+    out[4 + role] = acc.zz.c;
+    out[6 + role] = acc.zzz.c;
+}
+template <class F>
+static void msm_launch_accumulate(cudaStream_t st, const void *point_table, const uint32_t *sorted, const uint32_t *offsets, size_t nbk, const uint32_t *task_cnt,
+                                  const uint32_t *task_off, const uint32_t *order, size_t max_tasks, XYZZ<F> *buckets, XYZZ<F> *partials) {
+    if constexpr (sizeof(F) > 48) {
+        // measured at 2^22: 3 blocks of 128 per SM (168 registers, small spills) 63.95 ms, 2 blocks (254 registers, none) 66.0 ms,
+        // one thread per chain (k_msm_accumulate<fq2_t>, 255 registers, 1.5 KB frame) 67.8 ms
+        const size_t threads = 2 * (nbk + max_tasks);
+        k_msm_accumulate_pair<<<(unsigned)((threads + AccPairShape::THREADS - 1) / AccPairShape::THREADS), AccPairShape::THREADS, 0, st>>>(
+            (const Affine<fq2_t> *)point_table, sorted, offsets, (uint32_t)nbk, task_cnt, task_off, order, (uint32_t)max_tasks, buckets, partials);
+    } else {
+        k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + AccShape<F>::THREADS - 1) / AccShape<F>::THREADS), AccShape<F>::THREADS, 0, st>>>(
+            (const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk, task_cnt, task_off, order, (uint32_t)max_tasks, buckets, partials);
+    }
+}
+
 // Folds the partial sums of the split buckets.  A bucket with few partials (small multiexps cut every chain, so most
 // buckets have 2-4) is summed by one thread; one with many (bucket 1 of a witness, the few buckets the short top window
 // feeds) by a whole block: threads stride over its partials, then a shared-memory tree.
@@ -605,8 +677,7 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         ctx->launches += scan_u32<uint32_t>(st, size_hist, cap + 1, size_cur, nullptr, sums);
         ctx->launches += 9;  // digits x2, pick_cap, count_tasks, order_buckets, accumulate, combine_small, combine_big, window_combine
         k_msm_order_buckets<<<(unsigned)((nbk + 255) / 256), 256, 0, st>>>(offsets, (uint32_t)nbk, cap_dev, size_cur, order);
-        k_msm_accumulate<F><<<(unsigned)((nbk + max_tasks + AccShape<F>::THREADS - 1) / AccShape<F>::THREADS), AccShape<F>::THREADS, 0, st>>>((const Affine<F> *)point_table, sorted, offsets, (uint32_t)nbk,
-                                                                                      task_cnt, task_off, order, (uint32_t)max_tasks, buckets, partials);
+        msm_launch_accumulate<F>(st, point_table, sorted, offsets, nbk, task_cnt, task_off, order, max_tasks, buckets, partials);
         k_msm_combine_small<F><<<1024, 64, 0, st>>>(split_list, n_split, task_cnt, task_off, partials, buckets);
         const size_t big_smem = COMBINE_BIG_THREADS / 2 * sizeof(XYZZ<F>);  // one entry per lane pair: 24 KiB (G1) / 48 KiB (G2) of dynamic shared memory
         bool &opted_in = ctx->combine_smem_opt_in[sizeof(F) > 48 ? 1 : 0];
