@@ -83,6 +83,27 @@ def test_ntt_large_all_kinds_full_compare(worker, log_m):
         del got, want
 
 
+@pytest.mark.parametrize("log_m", list(range(12, 20)) + [25])
+def test_large_transform_kernels_on_every_tile_shape(log_m, monkeypatch):
+    """The radix-4 large-transform kernels (k_ntt_pass4: values in [0, 2r) between stages, in-place middle passes) on every pass
+    shape they are built for -- B200ZK_NTT_LARGE_FROM=12 sends 2^12..2^19 through them (passes of 6 / 7 / 8 / 9 stages, the
+    one-stage first round of an odd pass), 2^25 is the four-pass split 7 + 6 + 6 + 6 -- all kinds, every limb against the oracle."""
+    import zcash_gpu_thesis_b200 as zk
+
+    monkeypatch.setenv("B200ZK_NTT_LARGE_FROM", "12")
+    w = zk.Worker(0)  # the threshold is read when the context is created
+    try:
+        m = 1 << log_m
+        coeffs = util.random_fr_mont(util.rng(700 + log_m), m)
+        for kind, name in KINDS:
+            got = zk.ntt_host(w, coeffs, kind)
+            want = cref.fft(coeffs, kind, serial=log_m < 20)
+            assert np.array_equal(got, want), f"{name} at 2^{log_m}"
+            del got, want
+    finally:
+        w.close()
+
+
 def test_polynomial_arith(worker):
     """domain.rs:379-423: fft * fft -> ifft equals the schoolbook product (a sample of degree pairs < 70)."""
     import zcash_gpu_thesis_b200 as zk

@@ -601,7 +601,8 @@ static int msm_run_t(Ctx *ctx, const Bases *bases, size_t base_offset, const voi
         // Automatic for multiexps with fewer than 64 additions per resident thread (a Spend proof's multiexps, a strong-scaling
         // shard): measured on B200, two waves of tasks: G1 2^16 1.53 -> 1.26 ms, G2 61 300 points 5.9 -> 4.8 ms.  Large
         // multiexps are throughput-bound and keep whole buckets (splitting only adds partial sums to fold).
-        const size_t slots = (size_t)ctx->sm_count * AccShape<F>::MINBLOCKS * AccShape<F>::THREADS;
+        const size_t slots = sizeof(F) > 48 ? (size_t)ctx->sm_count * AccPairShape::MINBLOCKS * AccPairShape::THREADS / 2  // G2: a lane pair per chain
+                                            : (size_t)ctx->sm_count * AccShape<F>::MINBLOCKS * AccShape<F>::THREADS;
         double waves = refs_max < 64 * slots ? 2.0 : 0.0;
         if (const char *e = getenv("B200ZK_MSM_WAVES")) waves = atof(e);
         if (waves > 0) {
