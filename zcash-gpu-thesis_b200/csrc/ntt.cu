@@ -10,6 +10,7 @@
 // Twiddles omega^k are precomputed once per domain size and cached in the context.  Every butterfly is the
 // reference's (domain.rs:300-308): t = a[hi]*w; a[hi] = a[lo]-t; a[lo] += t, on canonical values, so the
 // output is bit-identical to serial_fft / parallel_fft.
+#include <algorithm>
 #include <cstdlib>
 #include "fp.cuh"
 #include "internal.h"
@@ -241,7 +242,7 @@ struct NttShape4 {
     static constexpr int MINBLOCKS = (768 / THREADS) < 1 ? 1 : (768 / THREADS);  // 24 resident warps: 80 registers
     static constexpr size_t SMEM = (size_t)2 * TILE * sizeof(uint4);
 };
-__device__ __forceinline__ uint32_t ntt_swz4(uint32_t e) { return e ^ ((e >> 2) & 4u); }  // bit 4 -> bit 2: conflict-free for every P >= 2
+__device__ __forceinline__ uint32_t ntt_swz4(uint32_t e) { return e ^ ((e >> 2) & 6u); }  // bits 3, 4 -> bits 1, 2: conflict-free for every P >= 1
 template <int TILE>
 __device__ __forceinline__ fr_t ntt_sm_load4(const uint4 *sm, uint32_t e) {
     const uint32_t w = ntt_swz4(e);
@@ -351,6 +352,9 @@ __global__ void __launch_bounds__(NttShape4<B, Q>::THREADS, NttShape4<B, Q>::MIN
     }
 }
 
+// (Measured and rejected: the same pass as a persistent kernel whose next tile travels HBM -> shared memory by cp.async into a
+// second buffer while the current one is computed -- 2^24 fft 3.56 against 3.11 ms: the second buffer halves what is left of L1
+// for the twiddles and adds a barrier and a shared-memory round trip per tile.)
 // n <= 4: one thread, the reference's loop as is (bit reversal, log n stages; domain.rs:272-315) with the scalings around it
 __global__ void k_ntt_tiny(fr_t *a, const fr_t *tw, const fr_t *g_pow, const fr_t *gi_pow, const fr_t *consts, uint32_t log_n, int kind) {
     const uint32_t n = 1u << log_n;
@@ -488,6 +492,11 @@ static int ntt_launch4(Ctx *ctx, const NttPass &p) {
 }
 template <bool FIRST>
 static int ntt_dispatch(Ctx *ctx, const NttPass &p, uint32_t B, uint32_t Q, uint32_t XB) {
+    if (XB == 2 && Q == 1) {
+        if (B == 6) return ntt_launch4<6, 1, FIRST>(ctx, p);
+        if (B == 7) return ntt_launch4<7, 1, FIRST>(ctx, p);
+        if (B == 8) return ntt_launch4<8, 1, FIRST>(ctx, p);
+    }
     if (XB == 2 && Q == 2) {
         if (B == 6) return ntt_launch4<6, 2, FIRST>(ctx, p);
         if (B == 7) return ntt_launch4<7, 2, FIRST>(ctx, p);
@@ -524,7 +533,7 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         return B200ZK_OK;
     }
     // Large transforms (work-bound): k_ntt_pass4, passes of 8 or 6 stages where possible (whole radix-4 rounds; an odd size gets
-    // one pass of 7), four adjacent columns per tile (128-byte runs in HBM).  Small ones (latency-bound: the time is the serial
+    // one pass of 7), two adjacent columns per tile (64-byte runs in HBM).  Small ones (latency-bound: the time is the serial
     // chain of one thread): k_ntt_pass with one butterfly per thread and stage, passes of at most 9 stages, columns only while
     // they leave two tiles per SM.
     const bool large = log_n >= (uint32_t)ctx->ntt_large_from && log_n >= 12;
@@ -562,6 +571,9 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         fr_t *dst = ps == 0 ? S : ps + 1 == npass ? A : S;
         p.out = dst;
         const uint32_t XB = large ? 2 : 1;
+        // large transforms: two columns per tile (512-element tiles, 128 threads, six blocks per SM: a barrier waits for four
+        // warps instead of eight and more tiles are in different phases; 2^24 fft 3.19 -> 3.11 ms against four columns)
+        if (large && B <= 8) Q = 1;
         st = ps == 0 ? ntt_dispatch<true>(ctx, p, B, Q, XB) : ntt_dispatch<false>(ctx, p, B, Q, XB);
         if (st) return st;
         src = dst;
