@@ -529,9 +529,9 @@ def flat_secondary(extra):
 
 def traffic_from_profile():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-    (profiles/r01_traffic.json); None when the capture does not match the precomputed-table configuration."""
+    (profiles/r02_traffic.json); None when the capture does not match the precomputed-table configuration."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         return {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "source": t["source"], "workload": t["workload"]}
     except Exception:
         return None
