@@ -178,11 +178,12 @@ __global__ void __launch_bounds__(256) k_msm_digits(const uint32_t *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ bucket accumulation
-// resident blocks per SM the accumulation kernel is compiled for: G1 3 x 128 threads at 168 registers, G2 2 x 128 at 255
-// (measured: G2 with 12 warps at 168 registers 81.7 vs 77.8 ms at 2^22; 9-10 warps through __maxnreg__ 98.8 / 116 ms)
+// resident blocks per SM the G1 accumulation kernel is compiled for: 4 x 128 threads at 128 registers (16 warps; round 2: 73.0 ms at
+// 2^24 against 73.9 with 3 x 128 at 168 registers -- the extra warps are worth more than the ~90 extra bytes of spills; 7 x 64
+// threads 73.7).  G2 runs on lane pairs (k_msm_accumulate_pair).
 template <class F> struct AccShape {
     static constexpr unsigned THREADS = 128;
-    static constexpr unsigned MINBLOCKS = sizeof(F) > 48 ? 2 : 3;
+    static constexpr unsigned MINBLOCKS = 4;
 };
 // Oversized buckets (witness scalars are full of 0/1/small values: half of a Sapling witness lands in bucket 1 of
 // window 0) are split into tasks of at most `cap` points so that no thread walks a bucket alone; the partial sums of a
