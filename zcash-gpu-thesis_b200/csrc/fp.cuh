@@ -304,7 +304,8 @@ struct __align__(16) Fp {
     }
     // a*b + c*d with ONE Montgomery reduction, for operands up to p (not only below it): T <= 2 p^2 < p R.  The lane-split Fq2
     // product (fq2.cuh fq2h_t) is such a sum on either lane -- a0 b0 + (p - a1) b1 and a0 b1 + a1 b0.
-    static __device__ __noinline__ Fp muladd2_call(Fp a, Fp b, Fp c, Fp d) {
+    static __device__ __noinline__ Fp muladd2_call(Fp a, Fp b, Fp c, Fp d) { return muladd2_inline(a, b, c, d); }
+    __device__ __forceinline__ static Fp muladd2_inline(const Fp &a, const Fp &b, const Fp &c, const Fp &d) {
         uint32_t T[2 * N], U[2 * N];
         mul_rows<N>(U, c.v, d.v);
         mul_rows<N>(T, a.v, b.v);

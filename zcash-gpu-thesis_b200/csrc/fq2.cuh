@@ -80,21 +80,26 @@ struct fq2h_t {
     __device__ __forceinline__ friend fq2h_t operator-(const fq2h_t &a, const fq2h_t &b) { return {a.c - b.c}; }
     __device__ __forceinline__ fq2h_t dbl() const { return {c.dbl()}; }
     __device__ __forceinline__ fq2h_t neg() const { return {c.neg()}; }
-    __device__ __forceinline__ friend fq2h_t operator*(const fq2h_t &a, const fq2h_t &b) {
+    // The exchange, the operand selection and the two-term product form ONE out-of-line body: a call passes two Fq values in and one
+    // out (the inlined form put 24 shuffles + 36 selects + the marshalling of four operands at every one of ~20 call sites: 136 KB of
+    // kernel, and ptxas moved ~2000 register copies to the multiplier pipe as IMAD.MOV).
+    static __device__ __noinline__ fq_t mul_call(fq_t a, fq_t b) {
         const bool odd = role() != 0;
-        const fq_t ap = partner(a.c), bp = partner(b.c);
+        const fq_t ap = partner(a), bp = partner(b);
         // X * b_mine + Y * b_partner:  even (X, Y) = (a0, q - a1),  odd (X, Y) = (a0, a1) with b_mine = b1, b_partner = b0
-        const fq_t X = pick(odd, ap, a.c);
-        const fq_t Y = pick(odd, a.c, ap.neg_raw());
-        return {fq_t::muladd2_call(X, b.c, Y, bp)};
+        const fq_t X = pick(odd, ap, a);
+        const fq_t Y = pick(odd, a, ap.neg_raw());
+        return fq_t::muladd2_inline(X, b, Y, bp);
     }
-    __device__ __forceinline__ fq2h_t sqr() const {
+    static __device__ __noinline__ fq_t sqr_call(fq_t a) {
         const bool odd = role() != 0;
-        const fq_t ap = partner(c);
-        const fq_t P = c + pick(odd, c, ap);      // even: a0 + a1      odd: a1 + a1
-        const fq_t Q = pick(odd, ap, c - ap);     // even: a0 - a1      odd: a0
-        return {fq_t::mul_call(P, Q)};
+        const fq_t ap = partner(a);
+        const fq_t P = a + pick(odd, a, ap);      // even: a0 + a1      odd: a1 + a1
+        const fq_t Q = pick(odd, ap, a - ap);     // even: a0 - a1      odd: a0
+        return fq_t::mul_inline(P, Q);
     }
+    __device__ __forceinline__ friend fq2h_t operator*(const fq2h_t &a, const fq2h_t &b) { return {mul_call(a.c, b.c)}; }
+    __device__ __forceinline__ fq2h_t sqr() const { return {sqr_call(c)}; }
 };
 
 }  // namespace b200zk
