@@ -31,9 +31,14 @@ __device__ __forceinline__ F mul_sub(const F &a, const F &b, const F &c, const F
 template <>  // measured: G1 MSM 2^24 81.1 -> 79.7 ms
 __device__ __forceinline__ fq_t mul_sub<fq_t>(const fq_t &a, const fq_t &b, const fq_t &c, const fq_t &d) { return fq_t::mulsub_call(a, b, c, d); }
 
-// (lane-split Fq2, fq2h_t: the generic form.  A four-product a*b - c*d under one reduction was measured twice -- as two calls
-// handing a 24-limb intermediate over, and as one out-of-line body: 156 multiplier instructions less per addition, but the row-wise
-// unreduced products and their 24-limb accumulations cost more than the reduction they save: G2 2^22 68.0 / 66.9 vs 63.95 ms.)
+template <>  // lane-split Fq2: four Fq products under one reduction on either lane (fq2.cuh)
+__device__ __forceinline__ fq2h_t mul_sub<fq2h_t>(const fq2h_t &a, const fq2h_t &b, const fq2h_t &c, const fq2h_t &d) {
+    return {fq2h_t::mulsub_call(a.c, b.c, c.c, d.c)};
+}
+// (Before the products were fused row by row (fp.cuh dot_inline), the four-product form lost:  as unreduced 2N-limb products added
+// up and reduced once it was measured twice -- as two calls handing a 24-limb intermediate over, and as one out-of-line body: 156
+// multiplier instructions less per addition, but the row-wise unreduced products and their 24-limb accumulations cost more than the
+// reduction they save: G2 2^22 68.0 / 66.9 vs 63.95 ms.)
 template <class F>
 struct XYZZ {
     F x, y, zz, zzz;

@@ -285,35 +285,66 @@ struct __align__(16) Fp {
     static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
     // Two independent products in one out-of-line body (used by the Fq2 product / squaring: one call instead of two,
     // 2 % on the G2 multiexp; pairing the products of the G1 point formulas the same way measured no gain).
-    // a*b - c*d with ONE Montgomery reduction: both products stay 2N limbs wide, T = a*b + (p^2 - c*d) < 2 p^2 < p R, and
-    // redc_wide brings it home (the Y3 of the point additions is such a difference: 156 multiplier instructions less).
-    // Only for parameter sets that define mod_sq (Fq).
-    static __device__ __noinline__ Fp mulsub_call(Fp a, Fp b, Fp c, Fp d) {
-        uint32_t T[2 * N], U[2 * N];
-        mul_rows<N>(U, c.v, d.v);
-        U[0] = sub_cc(P::mod_sq(0), U[0]);
-#pragma unroll
-        for (int k = 1; k < 2 * N - 1; k++) U[k] = subc_cc(P::mod_sq(k), U[k]);
-        U[2 * N - 1] = subc(P::mod_sq(2 * N - 1), U[2 * N - 1]);
-        mul_rows<N>(T, a.v, b.v);
-        T[0] = add_cc(T[0], U[0]);
-#pragma unroll
-        for (int k = 1; k < 2 * N - 1; k++) T[k] = addc_cc(T[k], U[k]);
-        T[2 * N - 1] = addc(T[2 * N - 1], U[2 * N - 1]);
-        return redc_wide(T);
-    }
+    // a*b - c*d with ONE Montgomery reduction (the Y3 of the point additions is such a difference: 156 multiplier instructions
+    // less than two products): a*b + (p - c)*d through the fused two-term rows below.  (Round 1 formed both products as unreduced
+    // 2N-limb values, T = a*b + (p^2 - c*d), and reduced T: the same multiplies, ~100 more additions and two 24-limb temporaries.)
+    // Only for Fq (see dot_inline).
+    static __device__ __noinline__ Fp mulsub_call(Fp a, Fp b, Fp c, Fp d) { return muladd2_inline(a, b, c.neg_raw(), d); }
     // a*b + c*d with ONE Montgomery reduction, for operands up to p (not only below it): T <= 2 p^2 < p R.  The lane-split Fq2
     // product (fq2.cuh fq2h_t) is such a sum on either lane -- a0 b0 + (p - a1) b1 and a0 b1 + a1 b0.
     static __device__ __noinline__ Fp muladd2_call(Fp a, Fp b, Fp c, Fp d) { return muladd2_inline(a, b, c, d); }
-    __device__ __forceinline__ static Fp muladd2_inline(const Fp &a, const Fp &b, const Fp &c, const Fp &d) {
-        uint32_t T[2 * N], U[2 * N];
-        mul_rows<N>(U, c.v, d.v);
-        mul_rows<N>(T, a.v, b.v);
-        T[0] = add_cc(T[0], U[0]);
+    // Fused like the single product (mad_n_redc): every row adds x_k * y_k[i] for ALL K terms to the even / odd accumulators, then
+    // m p, then shifts -- no 2N-limb intermediates, no separate additions.  A row leaves T < x_0 + .. + x_(K-1) + p <= (K + 1) p,
+    // and 2^32 (K + 1) p fits the accumulator pair (N + 1 limbs) while (K + 1) p < 2^(32 N): true for Fq up to K = 8
+    // (q / 2^384 = 0.10); the result is < p (1 + K p / R) < 2p, one conditional subtraction away from canonical.
+    template <int K>
+    __device__ __forceinline__ static void madk_n_redc(uint32_t *even, uint32_t *odd, const uint32_t *const (&x)[K], const uint32_t (&yi)[K], bool first) {
+        if (first) {
+            mul_n(odd, x[0] + 1, yi[0]);
+            mul_n(even, x[0], yi[0]);
+        } else {
+            even[0] = add_cc(even[0], odd[1]);
+            madc_n_rshift(odd, x[0] + 1, yi[0]);
+            cmad_n(even, x[0], yi[0]);
+            odd[N - 1] = addc(odd[N - 1], 0);
+        }
 #pragma unroll
-        for (int k = 1; k < 2 * N - 1; k++) T[k] = addc_cc(T[k], U[k]);
-        T[2 * N - 1] = addc(T[2 * N - 1], U[2 * N - 1]);
-        return redc_wide(T);
+        for (int k = 1; k < K; k++) {
+            cmad_n(odd, x[k] + 1, yi[k]);  // (its carry out of the top limb is zero: the whole sum fits)
+            cmad_n(even, x[k], yi[k]);
+            odd[N - 1] = addc(odd[N - 1], 0);
+        }
+        const uint32_t t0 = even[0];
+        uint32_t mi = mont_m(t0);
+        cmad_mod<1>(odd, mi, t0);
+        cmad_mod<0>(even, mi, t0);
+        odd[N - 1] = addc(odd[N - 1], 0);
+    }
+    // sum_k x_k * y_k under one reduction; operands up to p (not only below it)
+    template <int K>
+    __device__ __forceinline__ static Fp dot_inline(const uint32_t *const (&x)[K], const uint32_t *const (&y)[K]) {
+        static_assert(N == 12 && K <= 8, "the accumulator bound above is checked for Fq only");
+        uint32_t even[N], odd[N];
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            uint32_t y0[K], y1[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) { y0[k] = y[k][i]; y1[k] = y[k][i + 1]; }
+            madk_n_redc<K>(even, odd, x, y0, i == 0);
+            madk_n_redc<K>(odd, even, x, y1, false);
+        }
+        Fp r;
+        r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.v[i] = addc_cc(even[i], odd[i + 1]);
+        r.v[N - 1] = addc(even[N - 1], 0);
+        final_sub(r.v);
+        return r;
+    }
+    __device__ __forceinline__ static Fp muladd2_inline(const Fp &a, const Fp &b, const Fp &c, const Fp &d) {
+        const uint32_t *const x[2] = {a.v, c.v};
+        const uint32_t *const y[2] = {b.v, d.v};
+        return dot_inline<2>(x, y);
     }
     // p - a without the zero test: a value in (0, p] that stands for -a as an operand of muladd2_call
     __device__ __forceinline__ Fp neg_raw() const {
