@@ -104,6 +104,35 @@ def test_large_transform_kernels_on_every_tile_shape(log_m, monkeypatch):
         w.close()
 
 
+@pytest.mark.parametrize("log_m", [12, 16, 20])
+def test_large_transform_kernels_extreme_values(log_m, monkeypatch):
+    """The [0, 2r) value range of the large-transform kernels at its edges: vectors made of r - 1, 0 and 1 (as Montgomery residues,
+    i.e. the limbs themselves are r - 1 / 0 / 1) in long runs and alternating patterns, so that sums reach 2r - 2 + (2r - 1) and
+    differences -(2r - 1) at every stage; all kinds, every limb against the oracle."""
+    import zcash_gpu_thesis_b200 as zk
+
+    monkeypatch.setenv("B200ZK_NTT_LARGE_FROM", "12")
+    w = zk.Worker(0)
+    try:
+        m = 1 << log_m
+        top = np.array([(Fr.p - 1 >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+        one = np.array([1, 0, 0, 0], dtype=np.uint64)
+        r = util.rng(900 + log_m)
+        patterns = {
+            "all r-1": np.tile(top, (m, 1)),
+            "alternating r-1 / 0": np.where((np.arange(m) % 2 == 0)[:, None], top[None, :], np.zeros((1, 4), dtype=np.uint64)),
+            "random of {r-1, 0, 1}": np.stack([top, np.zeros(4, dtype=np.uint64), one])[r.integers(0, 3, size=m)],
+        }
+        for label, coeffs in patterns.items():
+            coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64)
+            for kind, name in KINDS:
+                got = zk.ntt_host(w, coeffs, kind)
+                want = cref.fft(coeffs, kind, serial=log_m < 20)
+                assert np.array_equal(got, want), f"{name} of '{label}' at 2^{log_m}"
+    finally:
+        w.close()
+
+
 def test_polynomial_arith(worker):
     """domain.rs:379-423: fft * fft -> ifft equals the schoolbook product (a sample of degree pairs < 70)."""
     import zcash_gpu_thesis_b200 as zk
