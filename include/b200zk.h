@@ -49,7 +49,9 @@ enum {
 };
 
 enum { B200ZK_G1 = 1, B200ZK_G2 = 2 };
-enum { B200ZK_FR = 0, B200ZK_FQ = 1, B200ZK_FQ2 = 2 /* c0 || c1, 12 u64 (fq2.rs) */ };
+enum { B200ZK_FR = 0, B200ZK_FQ = 1, B200ZK_FQ2 = 2 /* c0 || c1, 12 u64 (fq2.rs) */,
+       B200ZK_FQ2_PAIR = 3 /* the same elements computed by the lane-pair Fq2 of the G2 bucket accumulation (one component per lane):
+                              ADD, SUB, MUL, SQUARE, DOUBLE, NEGATE, and MULSUB on pairs of Fq2 elements */ };
 /* EvaluationDomain transforms, domain.rs:83-132 */
 enum { B200ZK_FFT = 0, B200ZK_IFFT = 1, B200ZK_COSET_FFT = 2, B200ZK_ICOSET_FFT = 3 };
 /* element-wise field ops (fr.rs / fq.rs); used by the parity tests and by EvaluationDomain::{mul,sub}_assign */
@@ -57,7 +59,7 @@ enum {
     B200ZK_OP_ADD = 0, B200ZK_OP_SUB = 1, B200ZK_OP_MUL = 2, B200ZK_OP_SQUARE = 3, B200ZK_OP_DOUBLE = 4,
     B200ZK_OP_NEGATE = 5, B200ZK_OP_INTO_REPR = 6, B200ZK_OP_FROM_REPR = 7, B200ZK_OP_INVERSE = 8,
     B200ZK_OP_INVERSE_BINARY = 9, /* same value as INVERSE, by the reference's binary extended Euclid (fq.rs:849-903) */
-    B200ZK_OP_MULSUB = 10 /* Fq only: a[i] = (p, q), b[i] = (r, s) pairs; out[i] = p q - r s (the fused Y3 of the point additions) */
+    B200ZK_OP_MULSUB = 10 /* Fq and FQ2_PAIR: a[i] = (p, q), b[i] = (r, s) pairs; out[i] = p q - r s (the fused Y3 of the point additions) */
 };
 /* point ops (ec.rs:296-526) for the parity tests */
 enum { B200ZK_POINT_DOUBLE = 0, B200ZK_POINT_ADD = 1, B200ZK_POINT_ADD_MIXED = 2 };

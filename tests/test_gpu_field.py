@@ -127,6 +127,46 @@ def test_fq2_ops_match_oracle_and_kats(worker):
         assert np.array_equal(got, _fq2_rows([el(k["out"])])), f"fq2.rs KAT {name}"
 
 
+def test_fq2_lane_pair_ops_match_oracle(worker):
+    """The lane-pair Fq2 of the G2 bucket accumulation (fq2.cuh fq2h_t: one component per lane, products as two-term sums under
+    one reduction, the four-product a b - c d) directly: every op on random + all edge pairs -- components 0, 1, q - 1, (q +- 1) / 2,
+    R, where the operand q - a1 of the product becomes q itself -- and the fq2.rs known answers."""
+    import json
+    import os
+
+    import zcash_gpu_thesis_b200 as zk
+    from oracle.fields import Fq2
+
+    r = util.rng(15)
+    edge = [0, 1, 2, Fq.p - 1, Fq.p - 2, (Fq.p - 1) // 2, (Fq.p + 1) // 2, Fq.R % Fq.p]
+    pairs = [(x, y) for x in edge for y in edge]
+    rnd = util.rows_to_ints(util.random_field_canonical(r, Fq.p, 2 * 3000, 6))
+    pairs += list(zip(rnd[0::2], rnd[1::2]))
+    other = pairs[::-1]
+    a, b = _fq2_rows(pairs), _fq2_rows(other)
+    for name, (code, fn) in dict(add=(0, Fq2.add), sub=(1, Fq2.sub), mul=(2, Fq2.mul)).items():
+        got = zk.field_vec(worker, zk.FQ2_PAIR, code, a, b)
+        assert np.array_equal(got, _fq2_rows([fn(x, y) for x, y in zip(pairs, other)])), name
+    for name, code, fn in (("square", 3, Fq2.sqr), ("double", 4, lambda x: Fq2.add(x, x)), ("negate", 5, Fq2.neg)):
+        got = zk.field_vec(worker, zk.FQ2_PAIR, code, a)
+        assert np.array_equal(got, _fq2_rows([fn(x) for x in pairs])), name
+    # p q - r s on quadruples: all edge pairs against each other, then random ones
+    quad = [(p_, q_, r_, s_) for p_ in pairs[:64:5] for q_ in pairs[1:64:7] for r_ in pairs[2:64:9] for s_ in pairs[3:64:11]]
+    quad += [(pairs[64 + 4 * i], pairs[65 + 4 * i], pairs[66 + 4 * i], pairs[67 + 4 * i]) for i in range(600)]
+    quad += [(x, y, x, y) for x, y in zip(pairs[:200], other[:200])]  # p q = r s: the difference is zero
+    pq = np.concatenate([_fq2_rows([t[0] for t in quad]), _fq2_rows([t[1] for t in quad])], axis=1)
+    rs = np.concatenate([_fq2_rows([t[2] for t in quad]), _fq2_rows([t[3] for t in quad])], axis=1)
+    got = zk.field_vec(worker, zk.FQ2_PAIR, zk._lib.OP_MULSUB, pq, rs)
+    want = _fq2_rows([Fq2.sub(Fq2.mul(t[0], t[1]), Fq2.mul(t[2], t[3])) for t in quad])
+    assert np.array_equal(got, want), "p q - r s"
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))["fq2"]
+    el = lambda v: (sum(int(x, 16) << (64 * i) for i, x in enumerate(v[0])), sum(int(x, 16) << (64 * i) for i, x in enumerate(v[1])))
+    for name, code in (("square", 3), ("mul", 2), ("add", 0), ("sub", 1), ("negate", 5), ("double", 4)):
+        k = kat[name]
+        got = zk.field_vec(worker, zk.FQ2_PAIR, code, _fq2_rows([el(k["a"])]), _fq2_rows([el(k["b"])]) if "b" in k else None)
+        assert np.array_equal(got, _fq2_rows([el(k["out"])])), f"fq2.rs KAT {name} on the lane pair"
+
+
 def test_fq_mulsub_matches_oracle(worker):
     """a b - c d with one Montgomery reduction (fp.cuh mulsub_call, the Y3 of every point addition): random and all edge
     quadruples, incl. a b = c d, c d = 0 and operands p - 1 (the q^2 - c d offset must never wrap)."""

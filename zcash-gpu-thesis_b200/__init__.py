@@ -52,4 +52,4 @@ from .bellman import (  # noqa: F401
     point_op,
 )
 from .generator import GeneratedParameters, KeypairAssembly, UnconstrainedVariable, generate_parameters  # noqa: F401
-from ._lib import G1, G2, FR, FQ, FQ2, FFT, IFFT, COSET_FFT, ICOSET_FFT  # noqa: F401
+from ._lib import G1, G2, FR, FQ, FQ2, FQ2_PAIR, FFT, IFFT, COSET_FFT, ICOSET_FFT  # noqa: F401

@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("B200ZK_LIB") or os.path.join(_HERE, "libb200zk.so")  
 
 OK, ERR_UNEXPECTED_IDENTITY, ERR_UNEXPECTED_EOF, ERR_DEGREE_TOO_LARGE, ERR_BAD_ARG, ERR_CUDA, ERR_NCCL, ERR_DECODE = range(8)
 G1, G2 = 1, 2
-FR, FQ, FQ2 = 0, 1, 2
+FR, FQ, FQ2, FQ2_PAIR = 0, 1, 2, 3
 FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
 OP_ADD, OP_SUB, OP_MUL, OP_SQUARE, OP_DOUBLE, OP_NEGATE, OP_INTO_REPR, OP_FROM_REPR, OP_INVERSE, OP_INVERSE_BINARY, OP_MULSUB = range(11)
 POINT_DOUBLE, POINT_ADD, POINT_ADD_MIXED = 0, 1, 2

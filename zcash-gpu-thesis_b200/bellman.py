@@ -682,8 +682,8 @@ def encode_points(worker, group, xy, inf=None, compressed=False) -> bytes:
 # ------------------------------------------------------------------------------------------------------ test / bench helpers
 def field_vec(worker, field, op, a, b=None):
     """element-wise Fr / Fq / Fq2 ops on host arrays; OP_MULSUB (Fq): rows of a are (p, q), rows of b are (r, s), out = p q - r s"""
-    w = {L.FR: 4, L.FQ: 6, L.FQ2: 12}[field]
-    wi = 2 * w if op == L.OP_MULSUB else w
+    w = {L.FR: 4, L.FQ: 6, L.FQ2: 12, L.FQ2_PAIR: 12}[field]
+    wi = 2 * w if op == L.OP_MULSUB else w  # (FQ2_PAIR MULSUB: rows of two Fq2 elements)
     a = _u64(a, wi)
     b = None if b is None else _u64(b, wi)
     out = np.empty((a.shape[0], w), dtype=np.uint64)

@@ -737,7 +737,7 @@ int b200zk_field_vec_dev(b200zk_ctx *ctx, int field, int op, const void *d_a, co
 
 int b200zk_field_vec(b200zk_ctx *ctx, int field, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
     CHECK_CTX(ctx);
-    if (field != B200ZK_FR && field != B200ZK_FQ && field != B200ZK_FQ2) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field");
+    if (field != B200ZK_FR && field != B200ZK_FQ && field != B200ZK_FQ2 && field != B200ZK_FQ2_PAIR) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad field");
     USE_DEVICE(ctx);
     const size_t ob = field == B200ZK_FR ? 32 : field == B200ZK_FQ ? 48 : 96;  // bytes per output element
     const size_t eb = op == B200ZK_OP_MULSUB ? 2 * ob : ob;                      // MULSUB reads pairs

@@ -58,9 +58,43 @@ __global__ void k_fq_mulsub(const fq_t *__restrict__ a, const fq_t *__restrict__
     out[i] = fq_t::mulsub_call(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
 }
 
+// The lane-pair Fq2 (fq2.cuh fq2h_t) on its own: two lanes per element, each holding one component.  MULSUB: a[i] = (p, q),
+// b[i] = (r, s) pairs of Fq2 elements, out[i] = p q - r s (the four-product Y3 of a G2 addition).
+__global__ void k_fq2_pair_vec(int op, const fq_t *__restrict__ a, const fq_t *__restrict__ b, fq_t *__restrict__ out, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const unsigned role = threadIdx.x & 1u;
+    if (i >= n) return;  // (both lanes of a pair leave together)
+    if (op == B200ZK_OP_MULSUB) {
+        const fq2h_t p{a[4 * i + role]}, q{a[4 * i + 2 + role]}, r{b[4 * i + role]}, s{b[4 * i + 2 + role]};
+        out[2 * i + role] = mul_sub(p, q, r, s).c;
+        return;
+    }
+    const fq2h_t x{a[2 * i + role]};
+    fq2h_t y{fq_t::zero()};
+    if (b) y.c = b[2 * i + role];
+    fq2h_t r;
+    switch (op) {
+    case B200ZK_OP_ADD: r = x + y; break;
+    case B200ZK_OP_SUB: r = x - y; break;
+    case B200ZK_OP_MUL: r = x * y; break;
+    case B200ZK_OP_SQUARE: r = x.sqr(); break;
+    case B200ZK_OP_DOUBLE: r = x.dbl(); break;
+    default: r = x.neg(); break;
+    }
+    out[2 * i + role] = r.c;
+}
+
 int launch_field_vec(Ctx *ctx, int field, int op, const void *a, const void *b, void *out, size_t n) {
     if (n == 0) return B200ZK_OK;
     unsigned blocks = (unsigned)((n + 127) / 128);
+    if (field == B200ZK_FQ2_PAIR) {
+        const bool ok = op == B200ZK_OP_ADD || op == B200ZK_OP_SUB || op == B200ZK_OP_MUL || op == B200ZK_OP_SQUARE || op == B200ZK_OP_DOUBLE ||
+                        op == B200ZK_OP_NEGATE || op == B200ZK_OP_MULSUB;
+        if (!ok) return set_error(ctx, B200ZK_ERR_BAD_ARG, "op not defined for the lane-pair Fq2");
+        k_fq2_pair_vec<<<(unsigned)((2 * n + 127) / 128), 128, 0, ctx->stream>>>(op, (const fq_t *)a, (const fq_t *)b, (fq_t *)out, n);
+        B200ZK_CUDA(ctx, cudaGetLastError());
+        return B200ZK_OK;
+    }
     if (op == B200ZK_OP_MULSUB) {
         if (field != B200ZK_FQ) return set_error(ctx, B200ZK_ERR_BAD_ARG, "MULSUB is an Fq op");
         k_fq_mulsub<<<blocks, 128, 0, ctx->stream>>>((const fq_t *)a, (const fq_t *)b, (fq_t *)out, n);
