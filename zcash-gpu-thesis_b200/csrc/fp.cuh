@@ -54,12 +54,6 @@ struct FrParams {
 };
 struct FqParams {
     static constexpr int N = 12;
-    __device__ __host__ static constexpr uint32_t mod_sq(int i) {  // q^2, 24 limbs (keeps the lazy Fq2 differences positive)
-        constexpr uint32_t m[24] = {0x1c718e39u, 0x26aa0000u, 0x76382eabu, 0x7ced6b1du, 0x62113cfdu, 0x162c3383u, 0x3e71b743u, 0x66bf91edu,
-                                    0x7091a049u, 0x292e85a8u, 0x86185c7bu, 0x1d68619cu, 0x0978ef01u, 0xf5314933u, 0x16ddca6eu, 0x50a62cfdu,
-                                    0x349e8bd0u, 0x66e59e49u, 0x0e7046b4u, 0xe2dc90e5u, 0xa22f25e9u, 0x4bd278eau, 0xb8c35fc7u, 0x02a437a4u};
-        return m[i];
-    }
     static constexpr uint32_t M0 = 0xfffcfffdu;  // low word of INV = 0x89f3fffcfffcfffd
     __device__ __host__ static constexpr uint32_t mod(int i) {
         constexpr uint32_t m[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
@@ -283,8 +277,6 @@ struct __align__(16) Fp {
     // ~10 KB function body keeps the hot loop inside the instruction cache; arguments and the result travel in
     // registers (no stack traffic).
     static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { return mul_inline(a, b); }
-    // Two independent products in one out-of-line body (used by the Fq2 product / squaring: one call instead of two,
-    // 2 % on the G2 multiexp; pairing the products of the G1 point formulas the same way measured no gain).
     // a*b - c*d with ONE Montgomery reduction (the Y3 of the point additions is such a difference: 156 multiplier instructions
     // less than two products): a*b + (p - c)*d through the fused two-term rows below.  (Round 1 formed both products as unreduced
     // 2N-limb values, T = a*b + (p^2 - c*d), and reduced T: the same multiplies, ~100 more additions and two 24-limb temporaries.)
@@ -355,10 +347,9 @@ struct __align__(16) Fp {
         r.v[N - 1] = subc(P::mod(N - 1), v[N - 1]);
         return r;
     }
+    // Two independent products in one out-of-line body (the Fq2 squaring: one call instead of two)
     struct Pair { Fp x, y; };
     static __device__ __noinline__ Pair mul2_call(Fp a, Fp b, Fp c, Fp d) { return {mul_inline(a, b), mul_inline(c, d)}; }
-    struct Triple { Fp x, y, z; };
-    static __device__ __noinline__ Triple mul3_call(Fp a, Fp b, Fp c, Fp d, Fp e, Fp f) { return {mul_inline(a, b), mul_inline(c, d), mul_inline(e, f)}; }
     __device__ __forceinline__ static Fp mul_inline(const Fp &a, const Fp &b) { return mul_inline_t<true>(a, b); }
     // CANONICAL = false: no final subtraction.  For a < p, b < 2p the result is < p (2p / R + 1) < 2p when 2p^2 < pR, true for Fr
     // (r / 2^256 = 0.453): the NTT keeps its values in [0, 2r) between stages and pays one subtraction at the very end.

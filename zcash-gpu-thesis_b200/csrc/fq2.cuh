@@ -22,10 +22,10 @@ struct fq2_t {
     // through local memory at every call (round 1: a 1552-byte stack frame and 97 M local loads in the G2 bucket accumulation)
     __device__ __forceinline__ friend fq2_t operator*(const fq2_t &a, const fq2_t &b) { return mul_call(a, b); }
     static __device__ __noinline__ fq2_t mul_call(fq2_t a, fq2_t b) {
-        // the three Karatsuba products in ONE out-of-line body (one call, three independent carry chains for ptxas to interleave):
-        // 2.5 % on the G2 multiexp against three separate calls
-        fq_t::Triple t = fq_t::mul3_call(a.c0, b.c0, a.c1, b.c1, a.c1 + a.c0, b.c0 + b.c1);
-        return {t.x - t.y, t.z - t.x - t.y};
+        // two two-term sums, each under ONE reduction (fp.cuh dot_inline): a0 b0 + (q - a1) b1  and  a0 b1 + a1 b0 -- 2 x 432 wide
+        // multiplies and no additions around them, against 3 x 300 + five additions for the reference's Karatsuba form
+        // (fq2.rs:118-132; round 1's mul3_call): G2 2^22 62.3 -> 61.6 ms, the 61 300-point G2 multiexp of a Spend proof 2.58 -> 2.44 ms.
+        return {fq_t::muladd2_inline(a.c0, b.c0, a.c1.neg_raw(), b.c1), fq_t::muladd2_inline(a.c0, b.c1, a.c1, b.c0)};
     }
     // fq2.rs:84-98
     __device__ __forceinline__ fq2_t sqr() const { return sqr_call(*this); }
