@@ -1,6 +1,8 @@
 // Fq2 = Fq[u]/(u^2+1) on the device: the coordinate field of G2.  Mirrors pairing::bls12_381::fq2
 // (fq2.rs:84-98 square = 2 Fq mul, :118-132 mul = 3 Fq mul (Karatsuba), add/sub/double/negate componentwise).
-// Results are canonical per component, hence bit-identical with the reference whatever formula is used.
+// Results are canonical per component, hence bit-identical with the reference whatever formula is used: here the product is two
+// two-term sums under one Montgomery reduction each (fp.cuh dot_inline), and the bucket accumulation splits an element over a
+// lane pair (fq2h_t below).
 #pragma once
 #include "fp.cuh"
 

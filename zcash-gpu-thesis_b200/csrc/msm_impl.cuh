@@ -11,9 +11,12 @@
 //                            (window, bucket) with global reductions
 //   2. scan                  exclusive prefix sum of the histogram = bucket offsets
 //   3. k_msm_digits<SCATTER> counting-sort of (base index, sign) by bucket
-//   4. k_msm_accumulate      one thread per bucket, XYZZ accumulator in registers, mixed adds (the hot loop)
-//   5. k_msm_reduce_level    bucket reduction sum (i+1)*S_i as an 8-ary tree of (R, A) pairs
+//   4. k_msm_accumulate      one thread per bucket (G1) / k_msm_accumulate_pair: one lane pair per bucket, one Fq component of
+//                            every Fq2 coordinate per lane (G2): XYZZ accumulator in registers, mixed adds (the hot loop);
+//                            oversized buckets are cut into tasks and folded by k_msm_combine_small / _big
+//   5. k_msm_ladder_step     bucket reduction sum (i+1)*S_i as a log-depth ladder on lane pairs, k_msm_ladder_final
 //   6. k_msm_window_combine  Horner over the windows (c doublings each), Jacobian result + status word
+// With the precomputed table 2^(c w) P (b200zk_bases_precompute) all windows feed ONE bucket set: steps 5 and 6 run once.
 //
 // Signed digits halve the bucket count (bucket ids 1..2^(c-1), negative digits add -P).  exp == 0 is skipped
 // and exp == 1 needs no special case: it is digit 1 of window 0.  The group result equals the reference's;
