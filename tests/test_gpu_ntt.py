@@ -205,6 +205,26 @@ def test_h_poly_matches_oracle(worker, n):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("n", [5000, 98785])
+def test_h_poly_batched_on_the_large_transform_kernels(n, monkeypatch):
+    """The H block runs its a / b / c transforms as ONE batch of launches (blockIdx.y = the vector); B200ZK_NTT_LARGE_FROM=12
+    sends them through the radix-4 kernels, whose batch strides differ between the caller's vectors and the scratch."""
+    import zcash_gpu_thesis_b200 as zk
+
+    monkeypatch.setenv("B200ZK_NTT_LARGE_FROM", "12")
+    w = zk.Worker(0)
+    try:
+        r = util.rng(450 + n)
+        a, b, c = (util.random_fr_mont(r, n) for _ in range(3))
+        m = 1
+        while m < n:
+            m *= 2
+        pad = lambda v: np.concatenate([v, np.zeros((m - n, 4), dtype=np.uint64)])
+        assert np.array_equal(zk.h_poly(w, a, b, c), cref.h_poly(pad(a), pad(b), pad(c)))
+    finally:
+        w.close()
+
+
 @pytest.mark.parametrize("n,shards", [(1, 3), (1000, 3), (98785, 3), (98785, 2), (5000, 1)])
 def test_h_poly_over_a_group_of_gpus(worker, n, shards):
     """b200zk_multi_h_poly: a, b, c transformed on separate GPUs of a one-process group (prover.rs:257-266 runs them as three

@@ -794,7 +794,7 @@ int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const u
     B200ZK_CUDA(ctx, cudaMemcpyAsync(s, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(s + bytes, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(s + 2 * bytes, c, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = ntt_h_poly(ctx, s, s + bytes, s + 2 * bytes, log_m, s + 3 * bytes);
+    rc = ntt_h_poly_batch(ctx, s, log_m, s + 3 * bytes, 1);  // a | b | c contiguous: the three transforms of a step in one set of launches
     if (rc) return rc;
     if (bytes > 32) B200ZK_CUDA(ctx, cudaMemcpyAsync(out, s + 3 * bytes, bytes - 32, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -93,6 +93,8 @@ int launch_microbench(Ctx *ctx, int kind, int iters, int blocks, int threads, vo
 // ntt.cu
 int ntt_get_tables(Ctx *ctx, uint32_t log_n, NttTables **out);
 int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind);
+int ntt_run_batch(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind, uint32_t batch, size_t stride);  // vector v at d_coeffs + v * stride elements
+int ntt_h_poly_batch(Ctx *ctx, void *d_abc, uint32_t log_n, void *d_out_repr, uint32_t K);            // a_0..a_(K-1) | b_0.. | c_0.. contiguous
 int ntt_distribute_powers(Ctx *ctx, void *d_coeffs, size_t n, const void *d_g);
 void ntt_free_all_tables(Ctx *ctx);
 int ntt_divide_by_z_on_coset(Ctx *ctx, void *d_coeffs, uint32_t log_n);

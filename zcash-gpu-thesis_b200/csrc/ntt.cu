@@ -76,6 +76,8 @@ struct NttPass {
     uint32_t log_n, s0;
     int pre_scale, post_scale;
     int last;             // the last pass of the transform (k_ntt_pass4 delivers canonical values only there)
+    size_t in_stride, out_stride;  // blockIdx.y = which vector of a batch of equal transforms: element offsets of its input / output
+    uint32_t batch;
 };
 
 struct FrPair { fr_t lo, hi; };
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(NttShape<B, Q, XB>::THREADS, NttShape<B, Q, XB
             for (int xi = 0; xi < E; xi++) {
                 const uint32_t g = gidx(e0 | ((uint32_t)xi << P));
                 const uint32_t src = FIRST ? __brev(g) >> (32 - log_n) : g;
-                x[xi] = p.in[src];
+                x[xi] = (p.in + (size_t)blockIdx.y * p.in_stride)[src];
                 if (FIRST && p.pre_scale) x[xi] = ntt_mul_call(x[xi], p.scale[src]);
             }
         } else if (!(XB == 1 && P - 1 < 5)) {  // (otherwise the previous round handed its elements over by warp shuffle)
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(NttShape<B, Q, XB>::THREADS, NttShape<B, Q, XB
                 const uint32_t g = gidx(e0 | ((uint32_t)xi << P));
                 if (p.post_scale == 1) x[xi] = ntt_mul_call(x[xi], p.scale[0]);
                 else if (p.post_scale == 2) x[xi] = ntt_mul_call(x[xi], p.scale[g]);
-                p.out[g] = x[xi];
+                (p.out + (size_t)blockIdx.y * p.out_stride)[g] = x[xi];
             }
         } else if (XB == 1 && P < 5) {
             // Warp-shuffle butterfly exchange.  The next stage pairs elements whose index differs in the bit this thread's id holds
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(NttShape4<B, Q>::THREADS, NttShape4<B, Q>::MIN
             for (int xi = 0; xi < 4; xi++) {
                 const uint32_t g = gidx(e0 | ((uint32_t)xi << P));
                 const uint32_t src = FIRST ? __brev(g) >> (32 - log_n) : g;
-                x[xi] = p.in[src];
+                x[xi] = (p.in + (size_t)blockIdx.y * p.in_stride)[src];
                 if (FIRST && p.pre_scale) x[xi] = ntt_mul_call(x[xi], p.scale[src]);
             }
         } else {
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(NttShape4<B, Q>::THREADS, NttShape4<B, Q>::MIN
                 if (p.post_scale == 1) x[xi] = ntt_mul_call(p.scale[0], x[xi]);        // (the product of a value < 2r is canonical)
                 else if (p.post_scale == 2) x[xi] = ntt_mul_call(p.scale[g], x[xi]);
                 else if (p.last) x[xi] = x[xi].canonical();
-                p.out[g] = x[xi];
+                (p.out + (size_t)blockIdx.y * p.out_stride)[g] = x[xi];
             }
         } else {
 #pragma unroll
@@ -475,7 +477,7 @@ static int ntt_launch(Ctx *ctx, const NttPass &p) {
         opted_in[ctx->device] = true;
     }
     const unsigned tiles = (unsigned)(((size_t)1 << p.log_n) >> S::T);
-    k_ntt_pass<B, Q, XB, FIRST><<<tiles, S::THREADS, S::SMEM, ctx->stream>>>(p);
+    k_ntt_pass<B, Q, XB, FIRST><<<dim3(tiles, p.batch), S::THREADS, S::SMEM, ctx->stream>>>(p);
     ctx->launches++;
     return B200ZK_OK;
 }
@@ -488,7 +490,7 @@ static int ntt_launch4(Ctx *ctx, const NttPass &p) {
         opted_in[ctx->device] = true;
     }
     const unsigned tiles = (unsigned)(((size_t)1 << p.log_n) >> S::T);
-    k_ntt_pass4<B, Q, FIRST><<<tiles, S::THREADS, S::SMEM, ctx->stream>>>(p);
+    k_ntt_pass4<B, Q, FIRST><<<dim3(tiles, p.batch), S::THREADS, S::SMEM, ctx->stream>>>(p);
     ctx->launches++;
     return B200ZK_OK;
 }
@@ -514,7 +516,13 @@ static int ntt_dispatch(Ctx *ctx, const NttPass &p, uint32_t B, uint32_t Q, uint
     return set_error(ctx, B200ZK_ERR_BAD_ARG, "internal: no NTT kernel for this pass shape");
 }
 
-int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
+int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) { return ntt_run_batch(ctx, d_coeffs, log_n, kind, 1, (size_t)1 << (log_n < 32 ? log_n : 0)); }
+
+// `batch` equal transforms in one set of launches (blockIdx.y = the vector): vector v starts at d_coeffs + v * stride elements.
+// The H blocks of a lock-step batch of proofs are such batches: 16 launches for K proofs instead of 16 K half-empty ones.
+int ntt_run_batch(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind, uint32_t batch, size_t stride) {
+    if (batch == 0) return B200ZK_OK;
+    if (batch > 65535) return set_error(ctx, B200ZK_ERR_BAD_ARG, "more than 65535 transforms in one batch");
     if (log_n >= 32) return set_error(ctx, B200ZK_ERR_DEGREE_TOO_LARGE, "log_m >= Fr::S (32)");  // domain.rs:59-61
     if (kind < B200ZK_FFT || kind > B200ZK_ICOSET_FFT) return set_error(ctx, B200ZK_ERR_BAD_ARG, "bad ntt kind");
     if (log_n == 0) return B200ZK_OK;  // m = 1: omega = 1, m^-1 = 1, g^0 = 1 -> every transform is the identity
@@ -529,8 +537,9 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
     const bool inverse = kind == B200ZK_IFFT || kind == B200ZK_ICOSET_FFT;
     const fr_t *tw = (const fr_t *)(inverse ? t->tw_inv : t->tw);
     if (log_n <= 2) {
-        k_ntt_tiny<<<1, 1, 0, ctx->stream>>>(A, tw, (const fr_t *)t->g_pow, (const fr_t *)t->gi_pow, (const fr_t *)t->consts, log_n, kind);
-        ctx->launches++;
+        for (uint32_t v = 0; v < batch; v++)
+            k_ntt_tiny<<<1, 1, 0, ctx->stream>>>(A + v * stride, tw, (const fr_t *)t->g_pow, (const fr_t *)t->gi_pow, (const fr_t *)t->consts, log_n, kind);
+        ctx->launches += batch;
         B200ZK_CUDA(ctx, cudaGetLastError());
         return B200ZK_OK;
     }
@@ -549,16 +558,16 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         for (uint32_t ps = (Bs[0] == 7 ? 1 : 0); ps < npass && rem >= 2; ps++) { Bs[ps] = 8; rem -= 2; }
         if (rem >= 2) { Bs[0] += 2; rem -= 2; }  // (7 -> 9; not reached for log_n <= 30)
     }
-    st = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, n * sizeof(fr_t));
+    st = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, (size_t)batch * n * sizeof(fr_t));
     if (st) return st;
-    fr_t *S = (fr_t *)ctx->scratch;
+    fr_t *S = (fr_t *)ctx->scratch;  // vector v of the batch at S + v * n
     uint32_t s0 = 0;
     const fr_t *src = A;
     for (uint32_t ps = 0; ps < npass; ps++) {
         NttPass p;
         const uint32_t B = Bs[ps];
         uint32_t Q = npass == 1 ? 0 : 2;
-        if (!large && Q && ((n >> (B + Q)) < (size_t)2 * ctx->sm_count || B + Q > 10)) Q = 0;
+        if (!large && Q && ((n >> (B + Q)) * batch < (size_t)2 * ctx->sm_count || B + Q > 10)) Q = 0;
         p.log_n = log_n;
         p.s0 = s0;
         p.tw = tw;
@@ -567,11 +576,14 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         p.post_scale = ps + 1 == npass ? (kind == B200ZK_IFFT ? 1 : kind == B200ZK_ICOSET_FFT ? 2 : 0) : 0;
         p.scale = p.pre_scale ? (const fr_t *)t->g_pow : p.post_scale == 2 ? (const fr_t *)t->gi_pow : (const fr_t *)t->consts + C_N_INV;
         p.in = src;
+        p.batch = batch;
+        p.in_stride = src == A ? stride : n;
         // The first pass gathers in bit-reversed order, so it writes to the other buffer; every later pass reads and writes the
         // same positions (a tile's reads all precede its first barrier, its writes follow the last), so the middle passes run in
         // place in the scratch buffer and the last one delivers into the caller's vector: no copy for any number of passes.
         fr_t *dst = ps == 0 ? S : ps + 1 == npass ? A : S;
         p.out = dst;
+        p.out_stride = dst == A ? stride : n;
         const uint32_t XB = large ? 2 : 1;
         // large transforms: two columns per tile (512-element tiles, 128 threads, six blocks per SM: a barrier waits for four
         // warps instead of eight and more tiles are in different phases; 2^24 fft 3.19 -> 3.11 ms against four columns)
@@ -581,7 +593,8 @@ int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) {
         src = dst;
         s0 += B;
     }
-    if (src != A) B200ZK_CUDA(ctx, cudaMemcpyAsync(A, src, n * sizeof(fr_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (src != A)  // (single-pass transforms only)
+        B200ZK_CUDA(ctx, cudaMemcpy2DAsync(A, stride * sizeof(fr_t), src, n * sizeof(fr_t), n * sizeof(fr_t), batch, cudaMemcpyDeviceToDevice, ctx->stream));
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
@@ -625,6 +638,24 @@ int ntt_h_poly_tail(Ctx *ctx, void *d_a, const void *d_b, const void *d_c, uint3
     k_h_combine<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((fr_t *)d_a, (const fr_t *)d_b, (const fr_t *)d_c, (const fr_t *)t->consts, n);
     if ((st = ntt_run(ctx, d_a, log_n, B200ZK_ICOSET_FFT))) return st;
     if (n > 1) k_into_repr<<<(unsigned)((n - 1 + 255) / 256), 256, 0, ctx->stream>>>((const fr_t *)d_a, (fr_t *)d_out_repr, n - 1);
+    B200ZK_CUDA(ctx, cudaGetLastError());
+    return B200ZK_OK;
+}
+
+// The H blocks of K proofs at once: d_abc = a_0 .. a_(K-1) | b_0 .. b_(K-1) | c_0 .. c_(K-1), each vector 2^log_n elements, contiguous;
+// d_out_repr = K vectors of 2^log_n slots (the first 2^log_n - 1 of each are the H coefficients in FrRepr form).
+int ntt_h_poly_batch(Ctx *ctx, void *d_abc, uint32_t log_n, void *d_out_repr, uint32_t K) {
+    int st;
+    const size_t n = (size_t)1 << log_n, total = (size_t)K * n;
+    fr_t *a = (fr_t *)d_abc, *b = a + total, *c = b + total;
+    NttTables *t;
+    if ((st = ntt_get_tables(ctx, log_n, &t))) return st;
+    if ((st = ntt_run_batch(ctx, a, log_n, B200ZK_IFFT, 3 * K, n))) return st;
+    if ((st = ntt_run_batch(ctx, a, log_n, B200ZK_COSET_FFT, 3 * K, n))) return st;
+    ctx->launches += 2;
+    k_h_combine<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(a, b, c, (const fr_t *)t->consts, total);
+    if ((st = ntt_run_batch(ctx, a, log_n, B200ZK_ICOSET_FFT, K, n))) return st;
+    k_into_repr<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(a, (fr_t *)d_out_repr, total);  // (slot n - 1 of a vector is not used)
     B200ZK_CUDA(ctx, cudaGetLastError());
     return B200ZK_OK;
 }
