@@ -797,10 +797,11 @@ def bench_spend_proofs(env, rng, shape=None):
     dt = _slowest_rank(time.perf_counter() - t0, world)
     for x in workers:
         x.close()
-    # the batch API: `lockstep` proofs share five batched multiexps (b200zk_groth16_prove_batch); two contexts alternate so
-    # that the uploads and the serial tails of one group overlap the multiexps of the other
+    # the batch API: `lockstep` proofs share five batched multiexps (b200zk_groth16_prove_batch); three contexts (host threads)
+    # alternate so that the uploads and the serial tails of one group overlap the multiexps of the others
+    # (measured: lock-step 8 x 2 contexts 387, 8 x 3 398, 16 x 2 393, 16 x 3 398, 4 x 4 392 proofs/s)
     lockstep = env_int("B200ZK_SPEND_LOCKSTEP", 8)
-    bstreams = env_int("B200ZK_SPEND_BATCH_STREAMS", 2)
+    bstreams = env_int("B200ZK_SPEND_BATCH_STREAMS", 3)
     groups = env_int("B200ZK_SPEND_GROUPS", 4)
     bworkers = [zk.Worker(w.device) for _ in range(bstreams)]
     ref = p0.write(w)
