@@ -31,11 +31,11 @@ __device__ __forceinline__ F mul_sub(const F &a, const F &b, const F &c, const F
 template <>  // measured: G1 MSM 2^24 81.1 -> 79.7 ms
 __device__ __forceinline__ fq_t mul_sub<fq_t>(const fq_t &a, const fq_t &b, const fq_t &c, const fq_t &d) { return fq_t::mulsub_call(a, b, c, d); }
 
-template <>  // lane-split Fq2: four Fq products under one reduction on either lane (fq2.cuh)
-__device__ __forceinline__ fq2h_t mul_sub<fq2h_t>(const fq2h_t &a, const fq2h_t &b, const fq2h_t &c, const fq2h_t &d) {
-    return {fq2h_t::mulsub_call(a.c, b.c, c.c, d.c)};
-}
-// (Before the products were fused row by row (fp.cuh dot_inline), the four-product form lost:  as unreduced 2N-limb products added
+// (lane-split Fq2, fq2h_t: the generic form.  With the row-fused products a four-product a*b - c*d under one reduction
+// (dot_inline<4>: 132 multiplier instructions less per addition) measures the same as two products and a subtraction, 61.6 ms at
+// 2^22 -- its 24 KB body pushes the hot path further out of the instruction cache (ncu: no_instruction 0.7 per issue) -- so the
+// smaller code stays.
+// Before the products were fused row by row (fp.cuh dot_inline), the four-product form lost outright:  as unreduced 2N-limb products added
 // up and reduced once it was measured twice -- as two calls handing a 24-limb intermediate over, and as one out-of-line body: 156
 // multiplier instructions less per addition, but the row-wise unreduced products and their 24-limb accumulations cost more than the
 // reduction they save: G2 2^22 68.0 / 66.9 vs 63.95 ms.)

@@ -100,17 +100,6 @@ struct fq2h_t {
         const fq_t Q = pick(odd, ap, a - ap);     // even: a0 - a1      odd: a0
         return fq_t::mul_inline(P, Q);
     }
-    // a * b - c * d as FOUR Fq products under one reduction (fp.cuh dot_inline<4>), exchange and selection inside the body:
-    //   even: a0 b0 + (q - a1) b1 + (q - c0) d0 + c1 d1        odd: a0 b1 + a1 b0 + (q - c0) d1 + (q - c1) d0
-    static __device__ __noinline__ fq_t mulsub_call(fq_t a, fq_t b, fq_t c, fq_t d) {
-        const bool odd = role() != 0;
-        const fq_t ap = partner(a), bp = partner(b), cp = partner(c), dp = partner(d);
-        const fq_t x0 = pick(odd, ap, a), x1 = pick(odd, a, ap.neg_raw());
-        const fq_t x2 = pick(odd, cp, c).neg_raw(), x3 = pick(odd, c.neg_raw(), cp);
-        const uint32_t *const x[4] = {x0.v, x1.v, x2.v, x3.v};
-        const uint32_t *const y[4] = {b.v, bp.v, d.v, dp.v};
-        return fq_t::dot_inline<4>(x, y);
-    }
     __device__ __forceinline__ friend fq2h_t operator*(const fq2h_t &a, const fq2h_t &b) { return {mul_call(a.c, b.c)}; }
     __device__ __forceinline__ fq2h_t sqr() const { return {sqr_call(c)}; }
 };
