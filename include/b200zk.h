@@ -217,6 +217,12 @@ int b200zk_multi_plan(const size_t *bounds, int n_dev, size_t base_offset, const
                       size_t *local_offset);
 
 /* ---- EvaluationDomain (bellman/src/domain.rs) -------------------------------------------------------------------- */
+/* Host-only helper (needs no device): how a transform of 2^log_m elements is cut into passes over HBM -- stages[i] butterfly stages
+ * and 2^columns_log[i] adjacent columns per tile in pass i, *radix4 = 1 for the large-transform kernels (radix-4 rounds), 0 for the
+ * latency-oriented ones.  `large_from` = the log2 size from which the large kernels are used (B200ZK_NTT_LARGE_FROM, default 20),
+ * `batch` = equal transforms launched together.  Arrays of 8 entries.  Returns the number of passes (0 for log_m outside 3..30:
+ * smaller transforms run in one thread).  The tests use it to check that every size maps to kernels the library was built with. */
+int b200zk_ntt_plan(uint32_t log_m, int large_from, int sm_count, uint32_t batch, uint32_t *stages, uint32_t *columns_log, int *radix4);
 /* In-place transform of m = 2^log_m Montgomery Fr coefficients, natural order in and out (domain.rs:83-132).
  * log_m >= 32 (= Fr::S) -> DEGREE_TOO_LARGE like from_coeffs (domain.rs:59-61). */
 int b200zk_ntt(b200zk_ctx *ctx, uint64_t *coeffs_host, uint32_t log_m, int kind);

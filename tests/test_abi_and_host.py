@@ -125,3 +125,31 @@ def test_product_synthesis_matches_the_oracle():
         x.alloc_input()
         circ.synthesize(x)
     assert asm.at_aux == oasm.at_aux and asm.bt_aux == oasm.bt_aux and asm.ct_inputs == oasm.ct_inputs and asm.num_constraints == oasm.num_constraints
+
+
+def test_every_transform_size_maps_to_built_kernels():
+    """b200zk_ntt_plan (host logic, no GPU): for every log_m the library accepts, with the default threshold, with the one the
+    tests use to force the large kernels and with the large kernels off, for single transforms and for the batches of the H
+    blocks -- the passes add up to log_m, each (stages, columns) pair is a kernel shape ntt.cu instantiates, a later pass never
+    has more columns than stage bits below it, and every pass has at least one tile."""
+    import zcash_gpu_thesis_b200 as zk
+
+    small = {(b, 2) for b in (5, 6, 7, 8)} | {(b, 0) for b in (5, 6, 7, 8, 9)}
+    small_first_only = {(3, 0), (4, 0)}
+    large = {(b, 1) for b in (6, 7, 8)} | {(b, 2) for b in (6, 7, 8, 9)}
+    for large_from in (20, 12, 31):
+        for batch in (1, 3, 24, 192):
+            for sm in (148, 132):
+                for log_m in range(3, 31):
+                    passes, radix4 = zk.ntt_plan(log_m, large_from, sm, batch)
+                    assert passes, (log_m, large_from)
+                    assert sum(b for b, _ in passes) == log_m
+                    assert radix4 == (log_m >= max(large_from, 12))
+                    s0 = 0
+                    for i, (b, q) in enumerate(passes):
+                        shapes = large if radix4 else (small | small_first_only if i == 0 else small)
+                        assert (b, q) in shapes, f"log_m {log_m}, large_from {large_from}: pass {i} = ({b}, {q}) is not a built kernel"
+                        assert i == 0 or s0 >= q
+                        assert log_m >= b + q
+                        s0 += b
+    assert zk.ntt_plan(2)[0] == [] and zk.ntt_plan(31)[0] == []

@@ -48,6 +48,7 @@ from .bellman import (  # noqa: F401
     verify_proofs,
     ShardedBases,
     multi_plan,
+    ntt_plan,
     ntt_host,
     point_op,
 )

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200zk_multi_job_wait": (_i, [_vp, _vp]),
     "b200zk_multi_h_poly": (_i, [_vp, _vp, _vp, _vp, _u32, _vp]),
     "b200zk_multi_plan": (_i, [_vp, _i, _sz, _vp, _sz, _vp, _vp]),
+    "b200zk_ntt_plan": (_i, [_u32, _i, _i, _u32, _vp, _vp, _vp]),
     "b200zk_ntt": (_i, [_vp, _vp, _u32, _i]),
     "b200zk_ntt_dev": (_i, [_vp, _vp, _u32, _i]),
     "b200zk_distribute_powers_dev": (_i, [_vp, _vp, _sz, _vp]),

@@ -679,6 +679,15 @@ def encode_points(worker, group, xy, inf=None, compressed=False) -> bytes:
     return out.tobytes()
 
 
+def ntt_plan(log_m, large_from=20, sm_count=148, batch=1):
+    """b200zk_ntt_plan (host logic only, needs no GPU): [(stages, columns_log), ...] per pass and whether the radix-4 kernels run"""
+    lib = L.load()
+    stages, cols = (C.c_uint32 * 8)(), (C.c_uint32 * 8)()
+    radix4 = C.c_int(0)
+    n = lib.b200zk_ntt_plan(log_m, large_from, sm_count, batch, stages, cols, C.byref(radix4))
+    return [(int(stages[i]), int(cols[i])) for i in range(n)], bool(radix4.value)
+
+
 # ------------------------------------------------------------------------------------------------------ test / bench helpers
 def field_vec(worker, field, op, a, b=None):
     """element-wise Fr / Fq / Fq2 ops on host arrays; OP_MULSUB (Fq): rows of a are (p, q), rows of b are (r, s), out = p q - r s"""

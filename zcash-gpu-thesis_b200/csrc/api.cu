@@ -783,6 +783,11 @@ int b200zk_h_poly_dev(b200zk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t
     return ntt_h_poly(ctx, d_a, d_b, d_c, log_m, d_out);
 }
 
+int b200zk_ntt_plan(uint32_t log_m, int large_from, int sm_count, uint32_t batch, uint32_t *stages, uint32_t *columns_log, int *radix4) {
+    if (!stages || !columns_log || !radix4 || log_m < 3 || log_m > 30 || batch == 0 || sm_count <= 0) return 0;
+    return (int)ntt_plan(log_m, large_from, sm_count, batch, stages, columns_log, radix4);
+}
+
 int b200zk_h_poly(b200zk_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint32_t log_m, uint64_t *out) {
     CHECK_CTX(ctx);
     if (log_m >= 32) return set_error(ctx, B200ZK_ERR_DEGREE_TOO_LARGE, "log_m >= Fr::S (32)");

@@ -92,6 +92,7 @@ int launch_point_op(Ctx *ctx, int group, int op, const void *a, const void *b, c
 int launch_microbench(Ctx *ctx, int kind, int iters, int blocks, int threads, void *out);
 // ntt.cu
 int ntt_get_tables(Ctx *ctx, uint32_t log_n, NttTables **out);
+uint32_t ntt_plan(uint32_t log_n, int large_from, int sm_count, uint32_t batch, uint32_t *B, uint32_t *Q, int *radix4);  // host logic: passes of a transform
 int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind);
 int ntt_run_batch(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind, uint32_t batch, size_t stride);  // vector v at d_coeffs + v * stride elements
 int ntt_h_poly_batch(Ctx *ctx, void *d_abc, uint32_t log_n, void *d_out_repr, uint32_t K);            // a_0..a_(K-1) | b_0.. | c_0.. contiguous

@@ -516,6 +516,34 @@ static int ntt_dispatch(Ctx *ctx, const NttPass &p, uint32_t B, uint32_t Q, uint
     return set_error(ctx, B200ZK_ERR_BAD_ARG, "internal: no NTT kernel for this pass shape");
 }
 
+// How a transform of 2^log_n elements is cut into passes (host logic only).  Large transforms (work-bound): k_ntt_pass4, passes of
+// 8 or 6 stages where possible (whole radix-4 rounds; an odd size gets one pass of 7), two adjacent columns per tile (64-byte runs
+// in HBM: 512-element tiles, 128 threads, six blocks per SM -- a barrier waits for four warps instead of eight and more tiles are in
+// different phases; 2^24 fft 3.19 -> 3.11 ms against four columns).  Small ones (latency-bound: the time is the serial chain of one
+// thread): k_ntt_pass with one butterfly per thread and stage, passes of at most 9 stages, four columns only while they leave two
+// tiles per SM.  Returns the number of passes; B[ps] stages and 2^Q[ps] columns per pass.
+uint32_t ntt_plan(uint32_t log_n, int large_from, int sm_count, uint32_t batch, uint32_t *B, uint32_t *Q, int *radix4) {
+    const size_t n = (size_t)1 << log_n;
+    const bool large = log_n >= (uint32_t)large_from && log_n >= 12;
+    uint32_t npass = (log_n + 8) / 9;
+    for (uint32_t ps = 0; ps < npass; ps++) B[ps] = log_n / npass + (ps < log_n % npass ? 1 : 0);
+    if (large && 6 * ((log_n + 7) / 8) <= log_n) {
+        npass = (log_n + 7) / 8;
+        uint32_t rem = log_n - 6 * npass;
+        for (uint32_t ps = 0; ps < npass; ps++) B[ps] = 6;
+        if (rem & 1) { B[0] = 7; rem--; }
+        for (uint32_t ps = (B[0] == 7 ? 1 : 0); ps < npass && rem >= 2; ps++) { B[ps] = 8; rem -= 2; }
+        if (rem >= 2) { B[0] += 2; rem -= 2; }  // (7 -> 9; not reached for log_n <= 30)
+    }
+    for (uint32_t ps = 0; ps < npass; ps++) {
+        Q[ps] = npass == 1 ? 0 : 2;
+        if (!large && Q[ps] && ((n >> (B[ps] + Q[ps])) * batch < (size_t)2 * sm_count || B[ps] + Q[ps] > 10)) Q[ps] = 0;
+        if (large && B[ps] <= 8) Q[ps] = 1;
+    }
+    *radix4 = large ? 1 : 0;
+    return npass;
+}
+
 int ntt_run(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind) { return ntt_run_batch(ctx, d_coeffs, log_n, kind, 1, (size_t)1 << (log_n < 32 ? log_n : 0)); }
 
 // `batch` equal transforms in one set of launches (blockIdx.y = the vector): vector v starts at d_coeffs + v * stride elements.
@@ -543,21 +571,9 @@ int ntt_run_batch(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind, uint32_t b
         B200ZK_CUDA(ctx, cudaGetLastError());
         return B200ZK_OK;
     }
-    // Large transforms (work-bound): k_ntt_pass4, passes of 8 or 6 stages where possible (whole radix-4 rounds; an odd size gets
-    // one pass of 7), two adjacent columns per tile (64-byte runs in HBM).  Small ones (latency-bound: the time is the serial
-    // chain of one thread): k_ntt_pass with one butterfly per thread and stage, passes of at most 9 stages, columns only while
-    // they leave two tiles per SM.
-    const bool large = log_n >= (uint32_t)ctx->ntt_large_from && log_n >= 12;
-    uint32_t npass = (log_n + 8) / 9, Bs[8];
-    for (uint32_t ps = 0; ps < npass; ps++) Bs[ps] = log_n / npass + (ps < log_n % npass ? 1 : 0);
-    if (large && 6 * ((log_n + 7) / 8) <= log_n) {
-        npass = (log_n + 7) / 8;
-        uint32_t rem = log_n - 6 * npass;
-        for (uint32_t ps = 0; ps < npass; ps++) Bs[ps] = 6;
-        if (rem & 1) { Bs[0] = 7; rem--; }
-        for (uint32_t ps = (Bs[0] == 7 ? 1 : 0); ps < npass && rem >= 2; ps++) { Bs[ps] = 8; rem -= 2; }
-        if (rem >= 2) { Bs[0] += 2; rem -= 2; }  // (7 -> 9; not reached for log_n <= 30)
-    }
+    uint32_t Bs[8], Qs[8];
+    int radix4 = 0;
+    const uint32_t npass = ntt_plan(log_n, ctx->ntt_large_from, ctx->sm_count, batch, Bs, Qs, &radix4);
     st = ensure_scratch(ctx, &ctx->scratch, &ctx->scratch_bytes, (size_t)batch * n * sizeof(fr_t));
     if (st) return st;
     fr_t *S = (fr_t *)ctx->scratch;  // vector v of the batch at S + v * n
@@ -565,9 +581,7 @@ int ntt_run_batch(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind, uint32_t b
     const fr_t *src = A;
     for (uint32_t ps = 0; ps < npass; ps++) {
         NttPass p;
-        const uint32_t B = Bs[ps];
-        uint32_t Q = npass == 1 ? 0 : 2;
-        if (!large && Q && ((n >> (B + Q)) * batch < (size_t)2 * ctx->sm_count || B + Q > 10)) Q = 0;
+        const uint32_t B = Bs[ps], Q = Qs[ps];
         p.log_n = log_n;
         p.s0 = s0;
         p.tw = tw;
@@ -584,10 +598,7 @@ int ntt_run_batch(Ctx *ctx, void *d_coeffs, uint32_t log_n, int kind, uint32_t b
         fr_t *dst = ps == 0 ? S : ps + 1 == npass ? A : S;
         p.out = dst;
         p.out_stride = dst == A ? stride : n;
-        const uint32_t XB = large ? 2 : 1;
-        // large transforms: two columns per tile (512-element tiles, 128 threads, six blocks per SM: a barrier waits for four
-        // warps instead of eight and more tiles are in different phases; 2^24 fft 3.19 -> 3.11 ms against four columns)
-        if (large && B <= 8) Q = 1;
+        const uint32_t XB = radix4 ? 2 : 1;
         st = ps == 0 ? ntt_dispatch<true>(ctx, p, B, Q, XB) : ntt_dispatch<false>(ctx, p, B, Q, XB);
         if (st) return st;
         src = dst;
